@@ -1,0 +1,1 @@
+from .. import constant_init, kaiming_init, xavier_init, normal_init  # noqa

@@ -1,0 +1,392 @@
+// tcgen05 / TMEM implicit-GEMM convolution for NHWC f16/bf16 activations (stride 1, "same"-style
+// zero padding), the tensor-core implementation of rv_conv2d.
+//
+// GEMM view per CTA tile: M = 128 output pixels (an 8 x 16 patch), N = NB output channels,
+// K = kw * (64-channel chunks of src0|src1) stages, each stage contributing kh taps x (<=4) UMMA_K=16
+// steps.  There is no im2col buffer:
+//   * A operand: for every (kx, channel-chunk) ONE TMA box load of (8+kh-1) x 16 pixels x 64
+//     channels at x-offset (x0 + kx - pad), y-offset (y0 - pad).  TMA's out-of-bounds zero fill
+//     implements the convolution's zero padding and the channel padding to 64.  The box lands in
+//     shared memory as 128-byte pixel rows with the 128B swizzle, i.e. directly in the canonical
+//     K-major UMMA layout; the kh vertical taps are row-shifted views of the same box
+//     (+ky*16 rows = +ky*2048 bytes, which preserves the swizzle phase).
+//   * B operand: weights pre-packed on the host in exactly the swizzled shared-memory image
+//     ([stage][ky][NB][64]), fetched with plain bulk copies; resident for the whole CTA lifetime when
+//     they fit, otherwise streamed through the same ring as A.
+//   * D: fp32 accumulators in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of
+//     tile i+1.  Persistent CTAs walk the tile list round-robin.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2-5 = epilogue
+// (tcgen05.ld -> bias/act/gate/residual -> NHWC or pixel-shuffled store).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace rv {
+
+static constexpr int TH = 8, TW = 16;
+static constexpr int MAX_SLOTS = 8;
+
+struct TcP {
+  int Ho, Wo, kh, kw, pad;
+  int nch0, nch1, c0, c1;
+  int S, NB, cout, tiles_x, tiles_y, slots, resident;
+  uint32_t a_bytes, w_bytes;
+  const uint8_t* wpack;
+  const float* bias;
+  int act_pre, act_post;
+  const void* gate;
+  int gate_cs;
+  const void* res;
+  int res_cs;
+  void* out;
+  int out_cs, pixel_shuffle, fmt, vec_ok;
+  uint32_t tmem_cols, acc_stride;
+};
+
+template <typename T>
+__device__ __forceinline__ void load16(const T* p, float v[16], bool vec) {
+  if (vec) {
+    if constexpr (sizeof(T) == 2) {
+      uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+      uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+      const T* ta = reinterpret_cast<const T*>(&a);
+      const T* tb = reinterpret_cast<const T*>(&b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i] = to_f(ta[i]); v[8 + i] = to_f(tb[i]); }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(p) + q);
+        v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = to_f(p[i]);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void store16(T* p, const float v[16]) {
+  if constexpr (sizeof(T) == 2) {
+    uint4 a, b;
+    T* ta = reinterpret_cast<T*>(&a);
+    T* tb = reinterpret_cast<T*>(&b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ta[i] = from_f<T>(v[i]); tb[i] = from_f<T>(v[8 + i]); }
+    reinterpret_cast<uint4*>(p)[0] = a;
+    reinterpret_cast<uint4*>(p)[1] = b;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
+
+template <typename TI, typename TR, typename TO>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+               const TcP p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[MAX_SLOTS], bar_empty[MAX_SLOTS], bar_w, bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[256];
+
+  const uint32_t raw = tc::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* smemA = smem;
+  uint8_t* smemW = smem + (size_t)p.slots * p.a_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = blockIdx.y;
+  const int ntiles = p.tiles_x * p.tiles_y;
+  const int nchunks = p.nch0 + p.nch1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.slots; ++i) {
+      tc::mbar_init(&bar_full[i], 1);
+      tc::mbar_init(&bar_empty[i], 1);
+    }
+    tc::mbar_init(&bar_w, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&bar_tfull[i], 1);
+      tc::mbar_init(&bar_tempty[i], 4);
+    }
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&tm0);
+    if (p.nch1) tc::prefetch_tmap(&tm1);
+  }
+  if (warp == 2) tc::tmem_alloc(&tmem_base_s, p.tmem_cols);
+  for (int i = threadIdx.x; i < p.NB; i += blockDim.x) {
+    int n = nblk * p.NB + i;
+    bias_s[i] = (n < p.cout) ? p.bias[n] : 0.f;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      const uint8_t* wsrc = p.wpack + (size_t)nblk * p.S * p.w_bytes;
+      if (p.resident) {
+        tc::mbar_expect_tx(&bar_w, (uint32_t)p.S * p.w_bytes);
+        for (int s = 0; s < p.S; ++s)
+          tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_w, smemW + (size_t)s * p.w_bytes, p.w_bytes);
+      }
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int y0 = (tile / p.tiles_x) * TH, x0 = (tile % p.tiles_x) * TW;
+        for (int s = 0; s < p.S; ++s, ++it) {
+          const int slot = it % p.slots;
+          const uint32_t ph = (it / p.slots) & 1u;
+          tc::mbar_wait(&bar_empty[slot], ph ^ 1u);
+          const int kx = s / nchunks, ch = s - kx * nchunks;
+          tc::mbar_expect_tx(&bar_full[slot], p.a_bytes + (p.resident ? 0u : p.w_bytes));
+          if (ch < p.nch0)
+            tc::tma_load_3d(&tm0, &bar_full[slot], smemA + (size_t)slot * p.a_bytes, ch * 64,
+                            x0 + kx - p.pad, y0 - p.pad);
+          else
+            tc::tma_load_3d(&tm1, &bar_full[slot], smemA + (size_t)slot * p.a_bytes,
+                            (ch - p.nch0) * 64, x0 + kx - p.pad, y0 - p.pad);
+          if (!p.resident)
+            tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_full[slot],
+                          smemW + (size_t)slot * p.w_bytes, p.w_bytes);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = tc::umma_idesc(p.fmt, 128, p.NB);
+      if (p.resident) {
+        tc::mbar_wait(&bar_w, 0);
+      }
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+        const uint32_t acc = t & 1u, accph = (t >> 1) & 1u;
+        tc::mbar_wait(&bar_tempty[acc], accph ^ 1u);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.S; ++s, ++it) {
+          const int slot = it % p.slots;
+          const uint32_t ph = (it / p.slots) & 1u;
+          tc::mbar_wait(&bar_full[slot], ph);
+          tc::tc_fence_after();
+          const int kx = s / nchunks, ch = s - kx * nchunks;
+          const int crem = (ch < p.nch0) ? (p.c0 - ch * 64) : (p.c1 - (ch - p.nch0) * 64);
+          const int ksteps = (min(crem, 64) + 15) >> 4;
+          const uint32_t a0 = tc::smem_u32(smemA + (size_t)slot * p.a_bytes);
+          const uint32_t b0 = tc::smem_u32(smemW + (size_t)(p.resident ? s : slot) * p.w_bytes);
+          for (int ky = 0; ky < p.kh; ++ky) {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = tc::umma_desc_sw128(a0 + ky * (TW * 128) + k * 32);
+              const uint64_t bd = tc::umma_desc_sw128(b0 + ky * (p.NB * 128) + k * 32);
+              tc::umma_f16(d_tmem, ad, bd, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          tc::umma_commit(&bar_empty[slot]);  // frees the smem slot when these MMAs retire
+        }
+        tc::umma_commit(&bar_tfull[acc]);
+      }
+    }
+  } else {
+    // ============================ epilogue ================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;
+    const int ty = m / TW, tx = m % TW;
+    const TI* gate = reinterpret_cast<const TI*>(p.gate);
+    const TR* res = reinterpret_cast<const TR*>(p.res);
+    TO* out = reinterpret_cast<TO*>(p.out);
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+      const uint32_t acc = t & 1u, accph = (t >> 1) & 1u;
+      const int oy = (tile / p.tiles_x) * TH + ty, ox = (tile % p.tiles_x) * TW + tx;
+      const bool valid = (oy < p.Ho) && (ox < p.Wo);
+      const size_t pix = (size_t)oy * p.Wo + ox;
+      tc::mbar_wait(&bar_tfull[acc], accph);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride;
+      for (int c0 = 0; c0 < p.NB; c0 += 16) {
+        uint32_t r[16];
+        tc::tmem_ld16(taddr + c0, r);
+        tc::tmem_ld_wait();
+        const int n0 = nblk * p.NB + c0;
+        if (!valid || n0 >= p.cout) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = apply_act(__uint_as_float(r[j]) + bias_s[c0 + j], p.act_pre);
+        const bool full = (n0 + 16 <= p.cout);
+        if (gate) {
+          if (full) {
+            float g[16];
+            load16<TI>(gate + pix * p.gate_cs + n0, g, p.vec_ok);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] *= g[j];
+          } else {
+            for (int j = 0; j < 16 && n0 + j < p.cout; ++j) v[j] *= to_f(gate[pix * p.gate_cs + n0 + j]);
+          }
+        }
+        if (res) {
+          if (full) {
+            float g[16];
+            load16<TR>(res + pix * p.res_cs + n0, g, p.vec_ok);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += g[j];
+          } else {
+            for (int j = 0; j < 16 && n0 + j < p.cout; ++j) v[j] += to_f(res[pix * p.res_cs + n0 + j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act_post);
+        if (p.pixel_shuffle) {
+          // n = 4c + 2a + b  ->  out[(2oy+a, 2ox+b)][c]; 16 n's = 4 consecutive c for each (a,b)
+          const int cb = n0 >> 2;
+#pragma unroll
+          for (int ab = 0; ab < 4; ++ab) {
+            const int a = ab >> 1, b = ab & 1;
+            TO* o = out + ((size_t)(2 * oy + a) * (2 * p.Wo) + (2 * ox + b)) * p.out_cs + cb;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              if (n0 + 4 * cc + ab < p.cout) o[cc] = from_f<TO>(v[4 * cc + ab]);
+          }
+        } else if (full && p.vec_ok) {
+          store16<TO>(out + pix * p.out_cs + n0, v);
+        } else {
+          for (int j = 0; j < 16 && n0 + j < p.cout; ++j) out[pix * p.out_cs + n0 + j] = from_f<TO>(v[j]);
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bar_tempty[acc]);
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+PFN_tmapEncodeTiled get_tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)f;
+  }
+  return fn;
+}
+
+static int make_act_tmap(CUtensorMap* m, const void* ptr, int C, int W, int H, int box_rows, int fmt) {
+  PFN_tmapEncodeTiled enc = get_tmap_encoder();
+  if (!enc) return fail(RV_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H};
+  cuuint64_t gstr[2] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)TW, (cuuint32_t)box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                   const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RV_E_CUDA, "cuTensorMapEncodeTiled failed (%d) C=%d W=%d H=%d", (int)r, C, W, H);
+  return RV_OK;
+}
+
+static int g_num_sms = 0;
+static int g_max_smem = 0;
+
+template <typename TI, typename TR, typename TO>
+static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& p, dim3 grid, size_t smem,
+                     cudaStream_t st) {
+  auto kern = conv_tc_kernel<TI, TR, TO>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    RV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    configured = g_max_smem;
+  }
+  kern<<<grid, 192, smem, st>>>(tm0, tm1, p);
+  RV_LAUNCH_CHECK("conv_tc");
+  return RV_OK;
+}
+
+int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
+  RV_REQUIRE(d->stride == 1, "rv_conv2d(tc): stride must be 1 (got %d)", d->stride);
+  RV_REQUIRE(d->in_dtype == RV_F16 || d->in_dtype == RV_BF16, "rv_conv2d(tc): activations must be f16/bf16");
+  RV_REQUIRE(d->c0 % 8 == 0 && (!d->src1 || d->c1 % 8 == 0), "rv_conv2d(tc): channel counts must be multiples of 8");
+  RV_REQUIRE(((uintptr_t)d->src0 % 16 == 0) && ((uintptr_t)d->src1 % 16 == 0) && ((uintptr_t)d->wpack % 16 == 0),
+             "rv_conv2d(tc): src/wpack must be 16-byte aligned");
+  RV_REQUIRE(d->nb >= 16 && d->nb <= 256 && d->nb % 16 == 0, "rv_conv2d(tc): nb=%d must be a multiple of 16 in [16,256]", d->nb);
+  RV_REQUIRE(d->kh >= 1 && d->kh <= 7 && d->kw >= 1 && d->kw <= 7, "rv_conv2d(tc): kernel size up to 7x7");
+  RV_REQUIRE(!d->pixel_shuffle || d->cout % 4 == 0, "rv_conv2d: pixel_shuffle needs cout %% 4 == 0");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    RV_CUDA_OK(cudaGetDevice(&dev));
+    RV_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    RV_CUDA_OK(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
+  TcP p;
+  p.Ho = d->H + 2 * d->pad - d->kh + 1;
+  p.Wo = d->W + 2 * d->pad - d->kw + 1;
+  RV_REQUIRE(p.Ho > 0 && p.Wo > 0, "rv_conv2d: empty output");
+  p.kh = d->kh; p.kw = d->kw; p.pad = d->pad;
+  p.c0 = d->c0; p.c1 = d->src1 ? d->c1 : 0;
+  p.nch0 = (p.c0 + 63) / 64; p.nch1 = (p.c1 + 63) / 64;
+  p.S = d->kw * (p.nch0 + p.nch1);
+  p.NB = d->nb; p.cout = d->cout;
+  p.tiles_x = (p.Wo + TW - 1) / TW; p.tiles_y = (p.Ho + TH - 1) / TH;
+  p.a_bytes = (uint32_t)(TH + d->kh - 1) * TW * 128;
+  p.w_bytes = (uint32_t)d->kh * p.NB * 128;
+  const int nblk = (d->cout + p.NB - 1) / p.NB;
+  // shared-memory plan: weights resident when they leave room for >= 3 A slots
+  const size_t budget = (size_t)g_max_smem - 1024 /*alignment*/ - 2048 /*static*/;
+  const size_t w_all = (size_t)p.S * p.w_bytes;
+  if (w_all + 3 * (size_t)p.a_bytes <= budget) {
+    p.resident = 1;
+    p.slots = (int)std::min<size_t>(MAX_SLOTS, (budget - w_all) / p.a_bytes);
+  } else {
+    p.resident = 0;
+    p.slots = (int)std::min<size_t>(MAX_SLOTS, budget / ((size_t)p.a_bytes + p.w_bytes));
+    RV_REQUIRE(p.slots >= 2, "rv_conv2d(tc): stage of %u bytes does not fit twice in shared memory",
+               p.a_bytes + p.w_bytes);
+  }
+  p.slots = std::min(p.slots, std::max(2, 2 * p.S));
+  const size_t smem = 1024 + (size_t)p.slots * p.a_bytes + (p.resident ? w_all : (size_t)p.slots * p.w_bytes);
+  p.wpack = (const uint8_t*)d->wpack; p.bias = d->bias;
+  p.act_pre = d->act_pre; p.act_post = d->act_post;
+  p.gate = d->gate; p.gate_cs = d->gate_cs; p.res = d->res; p.res_cs = d->res_cs;
+  p.out = d->out; p.out_cs = d->out_cs; p.pixel_shuffle = d->pixel_shuffle;
+  p.fmt = d->in_dtype == RV_BF16 ? 1 : 0;
+  const int rdt = d->res ? d->res_dtype : d->out_dtype;
+  auto al16 = [](const void* q, int cs, int dt) { return q == nullptr || (((uintptr_t)q % 16 == 0) && ((cs * dtype_size(dt)) % 16 == 0)); };
+  p.vec_ok = al16(d->out, d->out_cs, d->out_dtype) && al16(d->gate, d->gate_cs, d->in_dtype) && al16(d->res, d->res_cs, rdt);
+  p.acc_stride = (uint32_t)p.NB;
+  uint32_t cols = 32;
+  while (cols < 2u * p.NB) cols <<= 1;
+  p.tmem_cols = cols;
+
+  CUtensorMap tm0, tm1;
+  int rc = make_act_tmap(&tm0, d->src0, p.c0, d->W, d->H, TH + d->kh - 1, p.fmt);
+  if (rc) return rc;
+  if (p.nch1) {
+    rc = make_act_tmap(&tm1, d->src1, p.c1, d->W, d->H, TH + d->kh - 1, p.fmt);
+    if (rc) return rc;
+  } else {
+    tm1 = tm0;
+  }
+  const int ntiles = p.tiles_x * p.tiles_y;
+  int gx = std::min(ntiles, std::max(1, g_num_sms / nblk));
+  dim3 grid(gx, nblk);
+  if (d->in_dtype == RV_F16 && rdt == RV_F16 && d->out_dtype == RV_F16) return launch_tc<__half, __half, __half>(tm0, tm1, p, grid, smem, st);
+  if (d->in_dtype == RV_F16 && rdt == RV_F32 && d->out_dtype == RV_F32) return launch_tc<__half, float, float>(tm0, tm1, p, grid, smem, st);
+  if (d->in_dtype == RV_BF16 && rdt == RV_BF16 && d->out_dtype == RV_BF16) return launch_tc<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(tm0, tm1, p, grid, smem, st);
+  if (d->in_dtype == RV_BF16 && rdt == RV_F32 && d->out_dtype == RV_F32) return launch_tc<__nv_bfloat16, float, float>(tm0, tm1, p, grid, smem, st);
+  return fail(RV_E_UNSUPPORTED, "rv_conv2d(tc): unsupported dtype combination in=%d res=%d out=%d", d->in_dtype, rdt, d->out_dtype);
+}
+
+}  // namespace rv

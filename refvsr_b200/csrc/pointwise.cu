@@ -1,0 +1,661 @@
+// HBM/L2-bound kernels of the RefVSR hot path: image prep, SPyNet pyramid glue, flow warp,
+// reference gather / affine resampling, confidence-map glue and the reconstruction tail.
+// Every kernel is NHWC with 16-byte vector accesses where the channel count allows it.
+// Arithmetic follows SURVEY.md appendix A (verified against torch 2.11 by oracle/refvsr_oracle.py).
+#include "common.cuh"
+
+namespace rv {
+
+// ---------------------------------------------------------------------------------------------
+// small vector helpers: V elements of T moved as one 16/8/4-byte access
+// ---------------------------------------------------------------------------------------------
+template <typename T, int V>
+struct Vec {
+  T v[V];
+};
+template <typename T, int V>
+__device__ __forceinline__ Vec<T, V> ldv(const T* p) {
+  Vec<T, V> r;
+  if constexpr (sizeof(T) * V == 16) {
+    *reinterpret_cast<uint4*>(&r) = __ldg(reinterpret_cast<const uint4*>(p));
+  } else if constexpr (sizeof(T) * V == 8) {
+    *reinterpret_cast<uint2*>(&r) = __ldg(reinterpret_cast<const uint2*>(p));
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) r.v[i] = p[i];
+  }
+  return r;
+}
+template <typename T, int V>
+__device__ __forceinline__ void stv(T* p, const Vec<T, V>& r) {
+  if constexpr (sizeof(T) * V == 16) {
+    *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&r);
+  } else if constexpr (sizeof(T) * V == 8) {
+    *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(&r);
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) p[i] = r.v[i];
+  }
+}
+
+// torch.linspace(-1, 1, n)[i]  (symmetric evaluation, aten RangeFactories)
+__device__ __forceinline__ float linspace_m1_1(int i, int n) {
+  if (n == 1) return -1.f;
+  float step = 2.0f / (float)(n - 1);
+  return (i < n / 2) ? (-1.0f + step * (float)i) : (1.0f - step * (float)(n - 1 - i));
+}
+
+// aten area_pixel_compute_source_index for bilinear, align_corners=False
+__device__ __forceinline__ void bilin_src(int X, float scale, int in_size, int& i0, int& i1,
+                                          float& l1) {
+  float s = scale * ((float)X + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+}
+// align_corners=True variant: src = X * (in-1)/(out-1)
+__device__ __forceinline__ void bilin_src_ac(int X, float scale, int in_size, int& i0, int& i1,
+                                             float& l1) {
+  float s = scale * (float)X;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rv_prep_image
+// ---------------------------------------------------------------------------------------------
+struct Mat12 {
+  float m[12];
+  int use;
+};
+
+template <typename T>
+__global__ void prep_image_kernel(const float* __restrict__ src, int H, int W, Mat12 mat, int pool2,
+                                  T* __restrict__ out, int out_c) {
+  int Ho = pool2 ? H / 2 : H, Wo = pool2 ? W / 2 : W;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Ho * Wo) return;
+  int y = p / Wo, x = p % Wo;
+  float acc[3] = {0.f, 0.f, 0.f};
+  int n = pool2 ? 2 : 1;
+  for (int dy = 0; dy < n; ++dy)
+    for (int dx = 0; dx < n; ++dx) {
+      int sy = pool2 ? 2 * y + dy : y, sx = pool2 ? 2 * x + dx : x;
+      float r = src[(0 * H + sy) * W + sx], g = src[(1 * H + sy) * W + sx],
+            b = src[(2 * H + sy) * W + sx];
+      if (mat.use) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          acc[c] += mat.m[c * 4 + 0] * r + mat.m[c * 4 + 1] * g + mat.m[c * 4 + 2] * b +
+                    mat.m[c * 4 + 3];
+      } else {
+        acc[0] += r;
+        acc[1] += g;
+        acc[2] += b;
+      }
+    }
+  float inv = pool2 ? 0.25f : 1.f;
+  T* o = out + (size_t)p * out_c;
+  for (int c = 0; c < out_c; ++c) o[c] = from_f<T>(c < 3 ? acc[c] * inv : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SPyNet glue
+// ---------------------------------------------------------------------------------------------
+__global__ void spynet_resize_norm_kernel(const float* __restrict__ src, int H, int W,
+                                          float* __restrict__ out, int Ho, int Wo) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Ho * Wo) return;
+  int y = p / Wo, x = p % Wo;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilin_src(y, (float)H / (float)Ho, H, y0, y1, ly);
+  bilin_src(x, (float)W / (float)Wo, W, x0, x1, lx);
+  float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* s = src + (size_t)c * H * W;
+    float v = hy * (hx * s[y0 * W + x0] + lx * s[y0 * W + x1]) +
+              ly * (hx * s[y1 * W + x0] + lx * s[y1 * W + x1]);
+    out[(size_t)p * 3 + c] = (v - mean[c]) / stdv[c];
+  }
+}
+
+__global__ void avgpool2_kernel(const float* __restrict__ src, int H, int W, int C,
+                                float* __restrict__ out) {
+  int Ho = H / 2, Wo = W / 2;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Ho * Wo * C) return;
+  int c = i % C, p = i / C;
+  int y = p / Wo, x = p % Wo;
+  const float* s = src + ((size_t)(2 * y) * W + 2 * x) * C + c;
+  float v = s[0] + s[C] + s[(size_t)W * C] + s[(size_t)W * C + C];
+  out[i] = v * 0.25f;
+}
+
+template <typename T>
+__global__ void spynet_level_input_kernel(const float* __restrict__ ref,
+                                          const float* __restrict__ supp,
+                                          const float* __restrict__ flow_prev, int H, int W,
+                                          T* __restrict__ out8, float* __restrict__ flow_up) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W) return;
+  int y = p / W, x = p % W;
+  float fx = 0.f, fy = 0.f;
+  if (flow_prev != nullptr) {
+    int Hp = H / 2, Wp = W / 2;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    float sy = (H > 1) ? (float)(Hp - 1) / (float)(H - 1) : 0.f;
+    float sx = (W > 1) ? (float)(Wp - 1) / (float)(W - 1) : 0.f;
+    bilin_src_ac(y, sy, Hp, y0, y1, ly);
+    bilin_src_ac(x, sx, Wp, x0, x1, lx);
+    float hy = 1.f - ly, hx = 1.f - lx;
+    const float* f = flow_prev;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float v = hy * (hx * f[(y0 * Wp + x0) * 2 + c] + lx * f[(y0 * Wp + x1) * 2 + c]) +
+                ly * (hx * f[(y1 * Wp + x0) * 2 + c] + lx * f[(y1 * Wp + x1) * 2 + c]);
+      if (c == 0) fx = v * 2.0f; else fy = v * 2.0f;
+    }
+  }
+  flow_up[(size_t)p * 2 + 0] = fx;
+  flow_up[(size_t)p * 2 + 1] = fy;
+  // flow_warp(..., padding_mode='border', align_corners=True): flow_warp.py:36-46
+  float gx = 2.0f * ((float)x + fx) / (float)max(W - 1, 1) - 1.0f;
+  float gy = 2.0f * ((float)y + fy) / (float)max(H - 1, 1) - 1.0f;
+  float px = (gx + 1.f) * 0.5f * (float)(W - 1);
+  float py = (gy + 1.f) * 0.5f * (float)(H - 1);
+  px = fminf(fmaxf(px, 0.f), (float)(W - 1));
+  py = fminf(fmaxf(py, 0.f), (float)(H - 1));
+  float x0f = floorf(px), y0f = floorf(py);
+  int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+  float wx1 = px - x0f, wx0 = 1.f - wx1, wy1 = py - y0f, wy0 = 1.f - wy1;
+  T* o = out8 + (size_t)p * 8;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    o[c] = from_f<T>(ref[(size_t)p * 3 + c]);
+    float v = 0.f;
+    // nw, ne, sw, se (aten grid_sampler order)
+    v += supp[((size_t)y0 * W + x0) * 3 + c] * (wx0 * wy0);
+    if (x1 <= W - 1) v += supp[((size_t)y0 * W + x1) * 3 + c] * (wx1 * wy0);
+    if (y1 <= H - 1) v += supp[((size_t)y1 * W + x0) * 3 + c] * (wx0 * wy1);
+    if (x1 <= W - 1 && y1 <= H - 1) v += supp[((size_t)y1 * W + x1) * 3 + c] * (wx1 * wy1);
+    o[3 + c] = from_f<T>(v);
+  }
+  o[6] = from_f<T>(fx);
+  o[7] = from_f<T>(fy);
+}
+
+__global__ void flow_resize_kernel(const float* __restrict__ flow, int H, int W,
+                                   float* __restrict__ out, int h, int w) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= h * w) return;
+  int y = p / w, x = p % w;
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilin_src(y, (float)H / (float)h, H, y0, y1, ly);
+  bilin_src(x, (float)W / (float)w, W, x0, x1, lx);
+  float hy = 1.f - ly, hx = 1.f - lx;
+  float sc[2] = {(float)w / (float)W, (float)h / (float)H};
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    float v = hy * (hx * flow[((size_t)y0 * W + x0) * 2 + c] + lx * flow[((size_t)y0 * W + x1) * 2 + c]) +
+              ly * (hx * flow[((size_t)y1 * W + x0) * 2 + c] + lx * flow[((size_t)y1 * W + x1) * 2 + c]);
+    out[(size_t)p * 2 + c] = v * sc[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rv_warp : grid_sample(bilinear, zeros, align_corners=False) with the reference grid
+// one thread = one output pixel x one channel vector
+// ---------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void warp_kernel(const T* __restrict__ src, int Hi, int Wi, int C,
+                            const float* __restrict__ flow, int hf, int wf, int flow_up2,
+                            T* __restrict__ out) {
+  const int Ho = flow_up2 ? 2 * hf : hf, Wo = flow_up2 ? 2 * wf : wf;
+  const int cv = C / V;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Ho * Wo * cv) return;
+  int vc = (int)(i % cv);
+  int p = (int)(i / cv);
+  int Y = p / Wo, X = p % Wo;
+  float fx, fy;
+  if (flow_up2) {
+    int y0, y1, x0, x1;
+    float ly, lx;
+    float sy = (Ho > 1) ? (float)(hf - 1) / (float)(Ho - 1) : 0.f;
+    float sx = (Wo > 1) ? (float)(wf - 1) / (float)(Wo - 1) : 0.f;
+    bilin_src_ac(Y, sy, hf, y0, y1, ly);
+    bilin_src_ac(X, sx, wf, x0, x1, lx);
+    float hy = 1.f - ly, hx = 1.f - lx;
+    const float2* f2 = reinterpret_cast<const float2*>(flow);
+    float2 a = __ldg(f2 + y0 * wf + x0), b = __ldg(f2 + y0 * wf + x1), c = __ldg(f2 + y1 * wf + x0),
+           d = __ldg(f2 + y1 * wf + x1);
+    fx = (hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x)) * 2.0f;
+    fy = (hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y)) * 2.0f;
+  } else {
+    float2 f = __ldg(reinterpret_cast<const float2*>(flow) + p);
+    fx = f.x;
+    fy = f.y;
+  }
+  // models/utils.py:36-43
+  float gx = linspace_m1_1(X, Wo) + fx / (((float)Wi - 1.0f) / 2.0f);
+  float gy = linspace_m1_1(Y, Ho) + fy / (((float)Hi - 1.0f) / 2.0f);
+  // aten grid_sampler_unnormalize (align_corners=False)
+  float px = ((gx + 1.f) * (float)Wi - 1.f) / 2.f;
+  float py = ((gy + 1.f) * (float)Hi - 1.f) / 2.f;
+  float xw = floorf(px), yn = floorf(py);
+  int ix = (int)xw, iy = (int)yn;
+  float xe = xw + 1.f, ys = yn + 1.f;
+  float nw = (xe - px) * (ys - py), ne = (px - xw) * (ys - py), sw = (xe - px) * (py - yn),
+        se = (px - xw) * (py - yn);
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  const bool x0ok = ix >= 0 && ix < Wi, x1ok = ix + 1 >= 0 && ix + 1 < Wi;
+  const bool y0ok = iy >= 0 && iy < Hi, y1ok = iy + 1 >= 0 && iy + 1 < Hi;
+  const T* base = src + (size_t)vc * V;
+  if (y0ok && x0ok) {
+    Vec<T, V> t = ldv<T, V>(base + ((size_t)iy * Wi + ix) * C);
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] += to_f(t.v[k]) * nw;
+  }
+  if (y0ok && x1ok) {
+    Vec<T, V> t = ldv<T, V>(base + ((size_t)iy * Wi + ix + 1) * C);
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] += to_f(t.v[k]) * ne;
+  }
+  if (y1ok && x0ok) {
+    Vec<T, V> t = ldv<T, V>(base + ((size_t)(iy + 1) * Wi + ix) * C);
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] += to_f(t.v[k]) * sw;
+  }
+  if (y1ok && x1ok) {
+    Vec<T, V> t = ldv<T, V>(base + ((size_t)(iy + 1) * Wi + ix + 1) * C);
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] += to_f(t.v[k]) * se;
+  }
+  Vec<T, V> o;
+#pragma unroll
+  for (int k = 0; k < V; ++k) o.v[k] = from_f<T>(acc[k]);
+  stv<T, V>(out + (size_t)p * C + (size_t)vc * V, o);
+}
+
+// ---------------------------------------------------------------------------------------------
+// rv_patch_pack : one warp per pixel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+template <typename T>
+__global__ void patch_pack_kernel(const T* __restrict__ feat, int H, int W, int C, int mode,
+                                  __half* __restrict__ out, int kpad) {
+  const int K = C * 9;
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= H * W) return;
+  int y = warp / W, x = warp % W;
+  float vals[8];  // K <= 256
+  float ss = 0.f;
+  int nk = 0;
+  for (int k = lane; k < K; k += 32, ++nk) {
+    int c = k / 9, t = k % 9, ky = t / 3, kx = t % 3;
+    int sy = reflect1(y + ky - 1, H), sx = reflect1(x + kx - 1, W);
+    float v = to_f(feat[((size_t)sy * W + sx) * C + c]);
+    vals[nk] = v;
+    ss += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  float denom = fmaxf(sqrtf(ss), 1e-12f);
+  __half* row = out + (size_t)warp * kpad;
+  // zero the padding columns
+  int used = (mode == 0) ? K : 3 * K;
+  for (int k = used + lane; k < kpad; k += 32) row[k] = __float2half_rn(0.f);
+  nk = 0;
+  for (int k = lane; k < K; k += 32, ++nk) {
+    float v = vals[nk] / denom * 64.0f;
+    __half hi = __float2half_rn(v);
+    __half lo = __float2half_rn(v - __half2float(hi));
+    if (mode == 0) {
+      row[k] = hi;
+    } else if (mode == 1) {
+      row[k] = hi; row[K + k] = lo; row[2 * K + k] = hi;
+    } else {
+      row[k] = hi; row[K + k] = hi; row[2 * K + k] = lo;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rv_gather_blocks / rv_aligned_sample
+// ---------------------------------------------------------------------------------------------
+template <int BYTES>
+__global__ void gather_blocks_kernel(const uint8_t* __restrict__ value, int Hv, int Wv, int rowbytes,
+                                     const int32_t* __restrict__ idx, int hq, int wq, int ks,
+                                     uint8_t* __restrict__ out) {
+  const int Ho = ks * hq, Wo = ks * wq;
+  const int nv = rowbytes / BYTES;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Ho * Wo * nv) return;
+  int v = (int)(i % nv);
+  int p = (int)(i / nv);
+  int Y = p / Wo, X = p % Wo;
+  int ci = Y / ks, a = Y % ks, cj = X / ks, b = X % ks;
+  int r = __ldg(idx + ci * wq + cj);
+  int wvk = Wv / ks;
+  int ry = r / wvk, rx = r % wvk;
+  const uint8_t* s = value + ((size_t)(ks * ry + a) * Wv + (ks * rx + b)) * rowbytes + (size_t)v * BYTES;
+  uint8_t* d = out + (size_t)p * rowbytes + (size_t)v * BYTES;
+  if constexpr (BYTES == 16) *reinterpret_cast<uint4*>(d) = __ldg(reinterpret_cast<const uint4*>(s));
+  else if constexpr (BYTES == 8) *reinterpret_cast<uint2*>(d) = __ldg(reinterpret_cast<const uint2*>(s));
+  else if constexpr (BYTES == 4) *reinterpret_cast<uint32_t*>(d) = __ldg(reinterpret_cast<const uint32_t*>(s));
+  else *reinterpret_cast<uint16_t*>(d) = *reinterpret_cast<const uint16_t*>(s);
+}
+
+template <typename T, int V>
+__global__ void aligned_sample_kernel(const T* __restrict__ x, int h, int w, int ks, int C,
+                                      const float* __restrict__ affine, T* __restrict__ out) {
+  const int H = ks * h, W = ks * w, Hp = H + 2, Wp = W + 2;
+  const int cv = C / V;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)H * W * cv) return;
+  int vc = (int)(i % cv);
+  int p = (int)(i / cv);
+  int Y = p / W, X = p % W;
+  int ci = Y / ks, a = Y % ks, cj = X / ks, b = X % ks;
+  const float* af = affine + ((size_t)ci * w + cj) * 3;
+  float s_x = af[0], s_y = af[1], th = (af[2] - 1.0f) * 1.0472f;
+  float half = (float)((ks - 1) / 2) + 0.5f;  // -(ks-1)//2 - 0.5 + a  ==  a - half
+  float u = ((float)a - half) * s_x, v = ((float)b - half) * s_y;
+  float cs = cosf(th), sn = sinf(th);
+  float rr = u * cs - v * sn, cc = u * sn + v * cs;
+  float pr = rr + half + (float)(1 + ci * ks);
+  float pc = cc + half + (float)(1 + cj * ks);
+  float ltr = floorf(pr), ltc = floorf(pc);
+  float rbr = ltr + 1.f, rbc = ltc + 1.f;
+  const float Hm = (float)(Hp - 1), Wm = (float)(Wp - 1);
+  ltr = fminf(fmaxf(ltr, 0.f), Hm); rbr = fminf(fmaxf(rbr, 0.f), Hm);
+  ltc = fminf(fmaxf(ltc, 0.f), Wm); rbc = fminf(fmaxf(rbc, 0.f), Wm);
+  pr = fminf(fmaxf(pr, 0.f), Hm); pc = fminf(fmaxf(pc, 0.f), Wm);
+  float g_lt = (1.f + (ltr - pr)) * (1.f + (ltc - pc));
+  float g_rb = (1.f - (rbr - pr)) * (1.f - (rbc - pc));
+  float g_lb = (1.f + (ltr - pr)) * (1.f - (rbc - pc));
+  float g_rt = (1.f - (rbr - pr)) * (1.f + (ltc - pc));
+  // padded index -> source index (ReflectionPad2d(1))
+  int r0 = reflect1((int)ltr - 1, H), r1 = reflect1((int)rbr - 1, H);
+  int c0 = reflect1((int)ltc - 1, W), c1 = reflect1((int)rbc - 1, W);
+  const T* base = x + (size_t)vc * V;
+  Vec<T, V> t_lt = ldv<T, V>(base + ((size_t)r0 * W + c0) * C);
+  Vec<T, V> t_rb = ldv<T, V>(base + ((size_t)r1 * W + c1) * C);
+  Vec<T, V> t_lb = ldv<T, V>(base + ((size_t)r0 * W + c1) * C);
+  Vec<T, V> t_rt = ldv<T, V>(base + ((size_t)r1 * W + c0) * C);
+  Vec<T, V> o;
+#pragma unroll
+  for (int k = 0; k < V; ++k)
+    o.v[k] = from_f<T>(g_lt * to_f(t_lt.v[k]) + g_rb * to_f(t_rb.v[k]) + g_lb * to_f(t_lb.v[k]) +
+                       g_rt * to_f(t_rt.v[k]));
+  stv<T, V>(out + (size_t)p * C + (size_t)vc * V, o);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bicubic helpers (aten upsample_bicubic2d, align_corners=False, explicit scale factor)
+// ---------------------------------------------------------------------------------------------
+// planar source, bounded access
+__device__ __forceinline__ float bicubic_planar(const float* __restrict__ s, int H, int W, int Y,
+                                                int X, float inv_scale) {
+  float ry = inv_scale * ((float)Y + 0.5f) - 0.5f, rx = inv_scale * ((float)X + 0.5f) - 0.5f;
+  float fy = floorf(ry), fx = floorf(rx);
+  int iy = (int)fy, ix = (int)fx;
+  float wy[4], wx[4];
+  cubic_weights(ry - fy, wy);
+  cubic_weights(rx - fx, wx);
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int yy = clampi(iy - 1 + j, 0, H - 1);
+    const float* r = s + (size_t)yy * W;
+    float row = wx[0] * r[clampi(ix - 1, 0, W - 1)] + wx[1] * r[clampi(ix, 0, W - 1)] +
+                wx[2] * r[clampi(ix + 1, 0, W - 1)] + wx[3] * r[clampi(ix + 2, 0, W - 1)];
+    acc += wy[j] * row;
+  }
+  return acc;
+}
+
+template <typename T>
+__global__ void bicubic_up2_image_kernel(const float* __restrict__ src, int H, int W,
+                                         T* __restrict__ out, int out_c) {
+  int Ho = 2 * H, Wo = 2 * W;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Ho * Wo) return;
+  int Y = p / Wo, X = p % Wo;
+  T* o = out + (size_t)p * out_c;
+  for (int c = 0; c < out_c; ++c)
+    o[c] = from_f<T>(c < 3 ? bicubic_planar(src + (size_t)c * H * W, H, W, Y, X, 0.5f) : 0.f);
+}
+
+template <typename T>
+__global__ void conf_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, int h,
+                                 int w, int up2, T* __restrict__ out, int out_c) {
+  int Ho = up2 ? 2 * h : h, Wo = up2 ? 2 * w : w;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Ho * Wo) return;
+  float va, vb;
+  if (up2) {
+    int Y = p / Wo, X = p % Wo;
+    va = fminf(fmaxf(bicubic_planar(a, h, w, Y, X, 0.5f), 0.f), 1.f);
+    vb = fminf(fmaxf(bicubic_planar(b, h, w, Y, X, 0.5f), 0.f), 1.f);
+  } else {
+    va = a[p];
+    vb = b[p];
+  }
+  T* o = out + (size_t)p * out_c;
+  o[0] = from_f<T>(va);
+  o[1] = from_f<T>(vb);
+  for (int c = 2; c < out_c; ++c) o[c] = from_f<T>(0.f);
+}
+
+__global__ void conf_max_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                float* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fmaxf(a[i], b[i]);
+}
+
+template <typename T>
+__global__ void reconstruct_kernel(const T* __restrict__ x, int xc, const float* __restrict__ lr,
+                                   int h, int w, int scale, int clamp01,
+                                   float* __restrict__ out) {
+  int Ho = scale * h, Wo = scale * w;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Ho * Wo) return;
+  int Y = p / Wo, X = p % Wo;
+  float inv = 1.0f / (float)scale;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float base = bicubic_planar(lr + (size_t)c * h * w, h, w, Y, X, inv);
+    base = fminf(fmaxf(base, 0.f), 1.f);
+    float v = to_f(x[(size_t)p * xc + c]) + base;
+    if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+    out[(size_t)c * Ho * Wo + p] = v;
+  }
+}
+
+}  // namespace rv
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace rv;
+
+extern "C" int rv_prep_image(const float* src, int H, int W, const float* mat12_host, int pool2,
+                             void* out, int out_c, int out_dtype, void* stream) {
+  RV_REQUIRE(src && out && H > 0 && W > 0 && out_c >= 3, "rv_prep_image: bad arguments");
+  RV_REQUIRE(!pool2 || (H % 2 == 0 && W % 2 == 0), "rv_prep_image: pool2 needs even H,W (%d,%d)", H, W);
+  Mat12 m;
+  m.use = mat12_host != nullptr;
+  for (int i = 0; i < 12; ++i) m.m[i] = mat12_host ? mat12_host[i] : 0.f;
+  int n = (pool2 ? H / 2 : H) * (pool2 ? W / 2 : W);
+  RV_DISPATCH_DTYPE(out_dtype, T, (prep_image_kernel<T><<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      src, H, W, m, pool2, (T*)out, out_c)));
+  RV_LAUNCH_CHECK("prep_image");
+  return RV_OK;
+}
+
+extern "C" int rv_spynet_resize_norm(const float* src, int H, int W, float* out, int Ho, int Wo,
+                                     void* stream) {
+  RV_REQUIRE(src && out && H > 0 && W > 0 && Ho > 0 && Wo > 0, "rv_spynet_resize_norm: bad arguments");
+  spynet_resize_norm_kernel<<<cdiv(Ho * Wo, 256), 256, 0, (cudaStream_t)stream>>>(src, H, W, out, Ho, Wo);
+  RV_LAUNCH_CHECK("spynet_resize_norm");
+  return RV_OK;
+}
+
+extern "C" int rv_avgpool2(const float* src, int H, int W, int C, float* out, void* stream) {
+  RV_REQUIRE(src && out && H >= 2 && W >= 2 && C > 0, "rv_avgpool2: bad arguments");
+  int n = (H / 2) * (W / 2) * C;
+  avgpool2_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(src, H, W, C, out);
+  RV_LAUNCH_CHECK("avgpool2");
+  return RV_OK;
+}
+
+extern "C" int rv_spynet_level_input(const float* ref, const float* supp, const float* flow_prev,
+                                     int H, int W, void* out8, int out_dtype, float* flow_up,
+                                     void* stream) {
+  RV_REQUIRE(ref && supp && out8 && flow_up && H > 0 && W > 0, "rv_spynet_level_input: bad arguments");
+  RV_REQUIRE(flow_prev == nullptr || (H % 2 == 0 && W % 2 == 0),
+             "rv_spynet_level_input: level size must be even (%d,%d)", H, W);
+  RV_DISPATCH_DTYPE(out_dtype, T,
+                    (spynet_level_input_kernel<T><<<cdiv(H * W, 128), 128, 0, (cudaStream_t)stream>>>(
+                        ref, supp, flow_prev, H, W, (T*)out8, flow_up)));
+  RV_LAUNCH_CHECK("spynet_level_input");
+  return RV_OK;
+}
+
+extern "C" int rv_flow_resize(const float* flow, int H, int W, float* out, int h, int w, void* stream) {
+  RV_REQUIRE(flow && out && H > 0 && W > 0 && h > 0 && w > 0, "rv_flow_resize: bad arguments");
+  flow_resize_kernel<<<cdiv(h * w, 256), 256, 0, (cudaStream_t)stream>>>(flow, H, W, out, h, w);
+  RV_LAUNCH_CHECK("flow_resize");
+  return RV_OK;
+}
+
+template <typename T>
+static int warp_launch(const void* src, int Hi, int Wi, int C, const float* flow, int hf, int wf,
+                       int up2, void* out, cudaStream_t st) {
+  constexpr int VMAX = 16 / sizeof(T);
+  long long px = (long long)(up2 ? 4 : 1) * hf * wf;
+  bool aligned = ((uintptr_t)src % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  if (C % VMAX == 0 && aligned) {
+    long long n = px * (C / VMAX);
+    warp_kernel<T, VMAX><<<cdiv(n, 256), 256, 0, st>>>((const T*)src, Hi, Wi, C, flow, hf, wf, up2, (T*)out);
+  } else {
+    long long n = px * C;
+    warp_kernel<T, 1><<<cdiv(n, 256), 256, 0, st>>>((const T*)src, Hi, Wi, C, flow, hf, wf, up2, (T*)out);
+  }
+  RV_LAUNCH_CHECK("warp");
+  return RV_OK;
+}
+
+extern "C" int rv_warp(const void* src, int Hi, int Wi, int C, int dtype, const float* flow, int hf,
+                       int wf, int flow_up2, void* out, void* stream) {
+  RV_REQUIRE(src && flow && out && Hi > 1 && Wi > 1 && C > 0 && hf > 0 && wf > 0, "rv_warp: bad arguments");
+  RV_REQUIRE((uintptr_t)flow % 8 == 0, "rv_warp: flow must be 8-byte aligned");
+  RV_DISPATCH_DTYPE(dtype, T, return (warp_launch<T>(src, Hi, Wi, C, flow, hf, wf, flow_up2, out, (cudaStream_t)stream)));
+  return RV_OK;
+}
+
+extern "C" int rv_patch_pack(const void* feat, int H, int W, int C, int dtype, int mode, void* out,
+                             int kpad, void* stream) {
+  RV_REQUIRE(feat && out && H >= 2 && W >= 2, "rv_patch_pack: bad arguments");
+  RV_REQUIRE(C * 9 <= 256, "rv_patch_pack: C*9 must be <= 256 (got C=%d)", C);
+  RV_REQUIRE(mode >= 0 && mode <= 2, "rv_patch_pack: bad mode %d", mode);
+  RV_REQUIRE(kpad >= (mode == 0 ? 1 : 3) * C * 9, "rv_patch_pack: kpad %d too small", kpad);
+  long long threads = (long long)H * W * 32;
+  RV_DISPATCH_DTYPE(dtype, T, (patch_pack_kernel<T><<<cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+                                  (const T*)feat, H, W, C, mode, (__half*)out, kpad)));
+  RV_LAUNCH_CHECK("patch_pack");
+  return RV_OK;
+}
+
+extern "C" int rv_gather_blocks(const void* value, int Hv, int Wv, int C, int dtype,
+                                const int32_t* idx, int hq, int wq, int ks, void* out, void* stream) {
+  RV_REQUIRE(value && idx && out && ks >= 1 && Hv % ks == 0 && Wv % ks == 0 && hq > 0 && wq > 0,
+             "rv_gather_blocks: bad arguments");
+  int rowbytes = C * dtype_size(dtype);
+  long long px = (long long)ks * hq * ks * wq;
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint8_t* v = (const uint8_t*)value;
+  uint8_t* o = (uint8_t*)out;
+  bool a16 = ((uintptr_t)value % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  if (rowbytes % 16 == 0 && a16)
+    gather_blocks_kernel<16><<<cdiv(px * (rowbytes / 16), 256), 256, 0, st>>>(v, Hv, Wv, rowbytes, idx, hq, wq, ks, o);
+  else if (rowbytes % 4 == 0)
+    gather_blocks_kernel<4><<<cdiv(px * (rowbytes / 4), 256), 256, 0, st>>>(v, Hv, Wv, rowbytes, idx, hq, wq, ks, o);
+  else
+    gather_blocks_kernel<2><<<cdiv(px * (rowbytes / 2), 256), 256, 0, st>>>(v, Hv, Wv, rowbytes, idx, hq, wq, ks, o);
+  RV_LAUNCH_CHECK("gather_blocks");
+  return RV_OK;
+}
+
+template <typename T>
+static int aligned_sample_launch(const void* x, int h, int w, int ks, int C, const float* affine,
+                                 void* out, cudaStream_t st) {
+  constexpr int VMAX = 16 / sizeof(T);
+  long long px = (long long)ks * h * ks * w;
+  bool a16 = ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  if (C % VMAX == 0 && a16)
+    aligned_sample_kernel<T, VMAX><<<cdiv(px * (C / VMAX), 256), 256, 0, st>>>((const T*)x, h, w, ks, C, affine, (T*)out);
+  else
+    aligned_sample_kernel<T, 1><<<cdiv(px * C, 256), 256, 0, st>>>((const T*)x, h, w, ks, C, affine, (T*)out);
+  RV_LAUNCH_CHECK("aligned_sample");
+  return RV_OK;
+}
+
+extern "C" int rv_aligned_sample(const void* x, int h, int w, int ks, int C, int dtype,
+                                 const float* affine, void* out, void* stream) {
+  RV_REQUIRE(x && affine && out && h > 0 && w > 0 && ks >= 1 && C > 0, "rv_aligned_sample: bad arguments");
+  RV_REQUIRE(ks * h >= 2 && ks * w >= 2, "rv_aligned_sample: input too small for reflection padding");
+  RV_DISPATCH_DTYPE(dtype, T, return (aligned_sample_launch<T>(x, h, w, ks, C, affine, out, (cudaStream_t)stream)));
+  return RV_OK;
+}
+
+extern "C" int rv_bicubic_up2_image(const float* src, int H, int W, void* out, int out_c,
+                                    int out_dtype, void* stream) {
+  RV_REQUIRE(src && out && H > 0 && W > 0 && out_c >= 3, "rv_bicubic_up2_image: bad arguments");
+  RV_DISPATCH_DTYPE(out_dtype, T, (bicubic_up2_image_kernel<T><<<cdiv(4LL * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      src, H, W, (T*)out, out_c)));
+  RV_LAUNCH_CHECK("bicubic_up2_image");
+  return RV_OK;
+}
+
+extern "C" int rv_conf_pair(const float* a, const float* b, int h, int w, int up2, void* out,
+                            int out_c, int out_dtype, void* stream) {
+  RV_REQUIRE(a && b && out && h > 0 && w > 0 && out_c >= 2, "rv_conf_pair: bad arguments");
+  long long n = (long long)(up2 ? 4 : 1) * h * w;
+  RV_DISPATCH_DTYPE(out_dtype, T, (conf_pair_kernel<T><<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      a, b, h, w, up2, (T*)out, out_c)));
+  RV_LAUNCH_CHECK("conf_pair");
+  return RV_OK;
+}
+
+extern "C" int rv_conf_max(const float* a, const float* b, float* out, int n, void* stream) {
+  RV_REQUIRE(a && b && out && n > 0, "rv_conf_max: bad arguments");
+  conf_max_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
+  RV_LAUNCH_CHECK("conf_max");
+  return RV_OK;
+}
+
+extern "C" int rv_reconstruct(const void* x, int xc, int x_dtype, const float* lr, int h, int w,
+                              int scale, int clamp01, float* out, void* stream) {
+  RV_REQUIRE(x && lr && out && h > 0 && w > 0 && xc >= 3 && (scale == 2 || scale == 4),
+             "rv_reconstruct: bad arguments");
+  long long n = (long long)scale * h * scale * w;
+  RV_DISPATCH_DTYPE(x_dtype, T, (reconstruct_kernel<T><<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
+                                    (const T*)x, xc, lr, h, w, scale, clamp01, out)));
+  RV_LAUNCH_CHECK("reconstruct");
+  return RV_OK;
+}

@@ -1,0 +1,564 @@
+"""`Network` - the B200 implementation of models/archs/RefVSR.py::Network (reference lines cited inline).
+
+The module keeps the reference's constructor signature (`Network(config)`), attribute names,
+`state_dict()` schema and the stateful `forward(lrs, refs, is_first_frame, is_log, is_train)` contract
+(RefVSR.py:151-325).  The forward pass is an explicit schedule of calls into the operator set
+(`lib.CudaOps`: hand-written sm_100a kernels behind the C ABI).  Differences to the reference are
+confined to *how* results are obtained, never to what they are:
+
+  * activations are NHWC f16/bf16/f32 buffers; concat / bias / activation / gating / residual /
+    pixel-shuffle are fused into the conv kernels;
+  * exact reuse across sliding windows: optical flows, (conf, index) maps and reference
+    features are pure functions of frame content; a window that slides by one frame (the reference's own
+    assumption when it reuses forward_*_prev, RefVSR.py:256-260) re-computes only what the new frame
+    brings.  Flows the reference computes but never consumes are skipped;
+  * no gc.collect()/empty_cache() (RefVSR.py:206-208), no host synchronisation inside forward.
+"""
+import collections
+
+import torch
+import torch.nn as nn
+
+from . import packing
+from .lib import (ACT_CLAMP3, ACT_LRELU01, ACT_LRELU02, ACT_NONE, ACT_RELU)
+from .modules import build_parameter_tree
+
+_PREC = {'fp32': torch.float32, 'fp16': torch.float16, 'bf16': torch.bfloat16}
+
+
+def _cget(config, name, default):
+    try:
+        v = getattr(config, name)
+    except (AttributeError, KeyError):
+        return default
+    return default if v is None else v
+
+
+def _pad8(c):
+    return (c + 7) // 8 * 8
+
+
+class Network(nn.Module):
+    def __init__(self, config, ops=None):
+        super().__init__()
+        self.config = config
+        self.rank = torch.distributed.get_rank() if _cget(config, 'dist', False) else -1
+        self.scale = config.scale
+        self.flag_HD_in = config.flag_HD_in
+        self.mid_channels = config.mid_channels
+        if self.scale != 4 or self.flag_HD_in:
+            # RefVSR_*_8K (flag_HD_in, aa1 scale 4 / aa2 scale 8, VGG[0:7]) and the x2 models are the
+            # next rows of the scope table; fail loudly instead of silently computing something else.
+            raise NotImplementedError('refvsr_b200 round 1 implements the x4, flag_HD_in=False models '
+                                      '(config_RefVSR_{small_,}{L1,MFID}); got scale=%s flag_HD_in=%s'
+                                      % (self.scale, self.flag_HD_in))
+        build_parameter_tree(self, config)
+
+        # cross-call recurrent state (RefVSR.py:96-101), one entry per batch element
+        self.frame_itr_num = 0
+        self.max_frame_itr_num = config.reset_branch
+        self._state = {}
+        self._packed = {}
+        self._packed_key = None
+        self._ops = ops
+        prec = _cget(config, 'b200_precision', None)
+        if prec is None:
+            prec = 'fp16' if _cget(config, 'is_amp', False) else 'bf16'
+        self.precision = prec
+        self.act_dtype = _PREC[prec]
+        # 'split' = fp32-grade matching GEMM ([hi|lo|hi] fp16 operands), 'single' = one fp16 pass
+        # (what the reference does under autocast, trainers/trainer.py:237-239)
+        self.match_mode = _cget(config, 'b200_match', 'single' if prec == 'fp16' else 'split')
+        self.prefer_tc = bool(_cget(config, 'b200_tensor_cores', True))
+        self.reuse = bool(_cget(config, 'b200_reuse', True))
+        self._bufs = {}
+        self._device = torch.device('cpu')
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._packed.clear())
+
+    def _apply(self, fn, *a, **k):
+        # .to()/.cuda()/.half() move or convert parameters: packed kernels weights must be rebuilt
+        self._packed.clear()
+        self._bufs.clear()
+        self._state.clear()
+        return super()._apply(fn, *a, **k)
+
+    # ------------------------------------------------------------------------------------------
+    # plumbing
+    # ------------------------------------------------------------------------------------------
+    @property
+    def ops(self):
+        if self._ops is None:
+            from .lib import CudaOps
+            self._ops = CudaOps()
+        return self._ops
+
+    def set_ops(self, ops):
+        self._ops = ops
+        self._packed.clear()
+
+    def reset_state(self):
+        self._state.clear()
+        self.frame_itr_num = 0
+
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _layer(self, name, srcs, stride=1, pad=None, bias_add=0.0):
+        """Packed weights of conv `name` (attribute path under self) for the given source layout."""
+        key = (name, tuple(srcs))
+        hit = self._packed.get(key)
+        if hit is not None:
+            return hit
+        mod = self.get_submodule(name)
+        k = mod.weight.shape[2]
+        dev = self._device
+        pc = self.ops.pack_conv(name, mod.weight, mod.bias, list(srcs), stride, k // 2 if pad is None else pad,
+                                self.act_dtype, dev, self.prefer_tc, bias_add) \
+            if hasattr(self.ops, 'pack_conv') else \
+            packing.pack_conv(name, mod.weight, mod.bias, list(srcs), stride, k // 2 if pad is None else pad,
+                              self.act_dtype, dev, self.prefer_tc, bias_add)
+        self._packed[key] = pc
+        return pc
+
+    def _buf(self, tag, shape, dtype):
+        key = (tag, tuple(shape), dtype)
+        b = self._bufs.get(key)
+        if b is None or b.device != self._device:
+            b = torch.empty(tuple(shape), dtype=dtype, device=self._device)
+            self._bufs[key] = b
+        return b
+
+    def _conv(self, name, src0, src1, out, srcs, act_pre=ACT_NONE, act_post=ACT_NONE, gate=None, res=None,
+              pixel_shuffle=False, stride=1, pad=None, bias_add=0.0):
+        layer = self._layer(name, srcs, stride, pad, bias_add)
+        self.ops.conv2d(layer, src0, src1, out, gate=gate, res=res, act_pre=act_pre, act_post=act_post,
+                        pixel_shuffle=pixel_shuffle)
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # building blocks
+    # ------------------------------------------------------------------------------------------
+    def _reslist(self, prefix, n, x, out, tag):
+        """ResList (RefVSR_/common.py:64-82): n x [x + conv2(lrelu0.2(conv1(x)))], conv_tail, + input."""
+        C = x.shape[2]
+        H, W = x.shape[0], x.shape[1]
+        t = self._buf(tag + '.t', (H, W, C), x.dtype)
+        s = [self._buf(tag + '.s0', (H, W, C), x.dtype), self._buf(tag + '.s1', (H, W, C), x.dtype)]
+        cur = x
+        for i in range(n):
+            self._conv(f'{prefix}.RBs.{i}.conv1', cur, None, t, [(C, C)], act_pre=ACT_LRELU02)
+            nxt = s[i % 2]
+            self._conv(f'{prefix}.RBs.{i}.conv2', t, None, nxt, [(C, C)], res=cur)
+            cur = nxt
+        self._conv(f'{prefix}.conv_tail', cur, None, out, [(C, C)], res=x)
+        return out
+
+    def _prop_resblocks(self, prefix, lr8, feat, out, tag):
+        """ResidualBlocksWithInputConv (RefVSR.py:327-360) on cat[lr, feat] (RefVSR.py:225-226,266-267)."""
+        C = self.mid_channels
+        H, W = feat.shape[0], feat.shape[1]
+        nblk = self.config.num_blocks
+        t = self._buf(tag + '.t', (H, W, C), feat.dtype)
+        s = [self._buf(tag + '.s0', (H, W, C), feat.dtype), self._buf(tag + '.s1', (H, W, C), feat.dtype)]
+        cur = self._conv(f'{prefix}.main.0', lr8, feat, out if nblk == 0 else s[0], [(3, 8), (C, C)],
+                         act_pre=ACT_LRELU01)
+        for i in range(nblk):
+            self._conv(f'{prefix}.main.2.{i}.conv1', cur, None, t, [(C, C)], act_pre=ACT_RELU)
+            nxt = out if i == nblk - 1 else (s[1] if cur is s[0] else s[0])
+            self._conv(f'{prefix}.main.2.{i}.conv2', t, None, nxt, [(C, C)], res=cur)
+            cur = nxt
+        return out
+
+    # ---- SPyNet (SPyNet.py:49-139) ----------------------------------------------------------------
+    def _pyramid(self, img):
+        """img (3,h,w) fp32 -> list of 6 normalised levels, coarsest first, each (H,W,3) fp32."""
+        h, w = img.shape[1], img.shape[2]
+        w_up = w if w % 32 == 0 else 32 * (w // 32 + 1)
+        h_up = h if h % 32 == 0 else 32 * (h // 32 + 1)
+        lv = [torch.empty((h_up, w_up, 3), dtype=torch.float32, device=self._device)]
+        self.ops.spynet_resize_norm(img, lv[0])
+        for _ in range(5):
+            p = lv[-1]
+            q = torch.empty((p.shape[0] // 2, p.shape[1] // 2, 3), dtype=torch.float32, device=self._device)
+            self.ops.avgpool2(p, q)
+            lv.append(q)
+        return lv[::-1]
+
+    def _spynet(self, pyr_ref, pyr_supp, h, w):
+        """flow from ref to supp, (h,w,2) fp32.  pyr_*: outputs of _pyramid."""
+        dt = self.act_dtype
+        flow = None
+        for level in range(6):
+            r, s = pyr_ref[level], pyr_supp[level]
+            H, W = r.shape[0], r.shape[1]
+            x8 = self._buf('spy.x8', (H, W, 8), dt)
+            flow_up = torch.empty((H, W, 2), dtype=torch.float32, device=self._device)
+            self.ops.spynet_level_input(r, s, flow, x8, flow_up)
+            pre = f'FlowNet.basic_module.{level}.basic_module'
+            a = self._conv(f'{pre}.0.conv', x8, None, self._buf('spy.a', (H, W, 32), dt), [(8, 8)], act_pre=ACT_RELU)
+            b = self._conv(f'{pre}.1.conv', a, None, self._buf('spy.b', (H, W, 64), dt), [(32, 32)], act_pre=ACT_RELU)
+            c = self._conv(f'{pre}.2.conv', b, None, self._buf('spy.c', (H, W, 32), dt), [(64, 64)], act_pre=ACT_RELU)
+            d = self._conv(f'{pre}.3.conv', c, None, self._buf('spy.d', (H, W, 16), dt), [(32, 32)], act_pre=ACT_RELU)
+            flow = torch.empty((H, W, 2), dtype=torch.float32, device=self._device)
+            self._conv(f'{pre}.4.conv', d, None, flow, [(16, 16)], res=flow_up)   # flow_up + residue (SPyNet.py:95)
+        out = torch.empty((h, w, 2), dtype=torch.float32, device=self._device)
+        self.ops.flow_resize(flow, out)     # SPyNet.py:129-137; RefVSR.py:184,189 resize is the identity
+        return out
+
+    # ---- feature matching (attention.py:58-100) -----------------------------------------------------
+    def _match_features(self, img, pool2, tag):
+        sm = self.feature_match.sub_mean
+        wm = sm.weight.detach().float().reshape(3, 3).cpu()
+        bm = sm.bias.detach().float().cpu()
+        mat12 = [float(v) for r in range(3) for v in (wm[r, 0], wm[r, 1], wm[r, 2], bm[r])]
+        H, W = (img.shape[1] // 2, img.shape[2] // 2) if pool2 else (img.shape[1], img.shape[2])
+        dt = self.act_dtype
+        x8 = self._buf(tag + '.x8', (H, W, 8), dt)
+        self.ops.prep_image(img, x8, mat12=mat12, pool2=pool2)
+        f1 = self._conv('feature_match.feature_extract.0', x8, None, self._buf(tag + '.f1', (H, W, 64), dt),
+                        [(3, 8)], act_pre=ACT_RELU)
+        f2 = self._conv('feature_match.feature_extract.2', f1, None, self._buf(tag + '.f2', (H, W, 64), dt),
+                        [(64, 64)], act_pre=ACT_RELU)
+        f3 = self._conv('feature_match.feature_extract.map64.0', f2, None, self._buf(tag + '.f3', (H, W, 16), dt),
+                        [(64, 64)], act_pre=ACT_LRELU02)
+        return f3
+
+    def _feature_match(self, lr, ref):
+        """-> conf (h,w) fp32, idx (h*w,) int32 indexing the (hr/2 x wr/2) reference feature grid."""
+        h, w = lr.shape[1], lr.shape[2]
+        split = self.match_mode == 'split'
+        kpad = 448 if split else 192
+        lr_f = self._match_features(lr, False, 'fm.lr')
+        A = self._buf('fm.A', (h * w, kpad), torch.float16)
+        self.ops.patch_pack(lr_f, A, 1 if split else 0)
+        ref_f = self._match_features(ref, True, 'fm.ref')
+        R = ref_f.shape[0] * ref_f.shape[1]
+        B = self._buf('fm.B', (R, kpad), torch.float16)
+        self.ops.patch_pack(ref_f, B, 2 if split else 0)
+        conf = torch.empty((h, w), dtype=torch.float32, device=self._device)
+        idx = torch.empty((h * w,), dtype=torch.int32, device=self._device)
+        self.ops.match_argmax(A, B, conf, idx, impl=1 if self.prefer_tc else 0)
+        return conf, idx
+
+    # ---- reference encoders (RefVSR.py:233-234,274-275) ----------------------------------------------
+    def _ref_features(self, ref):
+        C, dt = self.mid_channels, self.act_dtype
+        hr, wr = ref.shape[1], ref.shape[2]
+        ref8 = torch.empty((hr, wr, 8), dtype=dt, device=self._device)
+        self.ops.prep_image(ref, ref8)
+        e0 = self._conv('ref_encoder1.0.0', ref8, None, self._buf('re.e0', (hr, wr, C), dt), [(3, 8)], act_pre=ACT_LRELU02)
+        e1 = self._conv('ref_encoder1.1.0', e0, None, self._buf('re.e1', (hr, wr, C), dt), [(C, C)], act_pre=ACT_LRELU02)
+        ref_feat = torch.empty((hr, wr, C), dtype=dt, device=self._device)
+        self._reslist('res1', 4, e1, ref_feat, 're.r1')
+        h2, w2 = (hr - 1) // 2 + 1, (wr - 1) // 2 + 1
+        d0 = self._conv('ref_encoder2.0.0', ref_feat, None, self._buf('re.d0', (h2, w2, C), dt), [(C, C)],
+                        act_pre=ACT_LRELU02, stride=2)
+        d1 = self._conv('ref_encoder2.1.0', d0, None, self._buf('re.d1', (h2, w2, C), dt), [(C, C)], act_pre=ACT_LRELU02)
+        ref_feat_down = torch.empty((h2, w2, C), dtype=dt, device=self._device)
+        self._reslist('res2', 4, d1, ref_feat_down, 're.r2')
+        return ref8, ref_feat, ref_feat_down
+
+    # ---- AlignedConv2d (alignment.py:39-100) --------------------------------------------------------
+    def _align_conv1(self, x8, out, tag):
+        H, W = x8.shape[0], x8.shape[1]
+        dt = self.act_dtype
+        a = self._conv('aa2.align.conv1.0', x8, None, self._buf(tag + '.a', (H, W, 32), dt), [(3, 8)],
+                       act_pre=ACT_LRELU02, pad=2)
+        t = self._conv('aa2.align.conv1.2.conv1', a, None, self._buf(tag + '.t', (H, W, 32), dt), [(32, 32)],
+                       act_pre=ACT_LRELU02)
+        self._conv('aa2.align.conv1.2.conv2', t, None, out, [(32, 32)], res=a, act_post=ACT_LRELU02)
+        return out
+
+    def _aa2(self, lr, ref8, idx, ref_feat, h, w):
+        """AlignedAttention scale=2 + AlignedConv2d (attention.py:131-159): -> (2h,2w,C)."""
+        C, dt = self.mid_channels, self.act_dtype
+        ks = self.aa2.scale
+        H2, W2 = 2 * h, 2 * w
+        warped = self._buf('aa2.wf', (H2, W2, C), dt)
+        self.ops.gather_blocks(ref_feat, idx, h, w, ks, warped)
+        wref8 = self._buf('aa2.wr', (H2, W2, 8), dt)
+        self.ops.gather_blocks(ref8, idx, h, w, ks, wref8)
+        q8 = self._buf('aa2.q8', (H2, W2, 8), dt)
+        self.ops.bicubic_up2_image(lr, q8)                       # alignment.py:41 (no clamp)
+        qf = self._align_conv1(q8, self._buf('aa2.qf', (H2, W2, 32), dt), 'aa2.c1q')
+        rf = self._align_conv1(wref8, self._buf('aa2.rf', (H2, W2, 32), dt), 'aa2.c1r')
+        ha, wa = (H2 + 4 - 5) // ks + 1, (W2 + 4 - 5) // ks + 1
+        p0 = self._conv('aa2.align.p_conv.0', rf, qf, self._buf('aa2.p0', (ha, wa, 32), dt), [(32, 32), (32, 32)],
+                        act_pre=ACT_LRELU02, stride=ks, pad=2)
+        pt = self._conv('aa2.align.p_conv.2.conv1', p0, None, self._buf('aa2.pt', (ha, wa, 32), dt), [(32, 32)],
+                        act_pre=ACT_LRELU02)
+        p1 = self._conv('aa2.align.p_conv.2.conv2', pt, None, self._buf('aa2.p1', (ha, wa, 32), dt), [(32, 32)],
+                        res=p0, act_post=ACT_LRELU02)
+        affine = self._buf('aa2.aff', (ha, wa, 3), torch.float32)
+        self._conv('aa2.align.p_conv.4', p1, None, affine, [(32, 32)], act_post=ACT_CLAMP3, pad=0, bias_add=1.0)
+        out = self._buf('aa2.out', (H2, W2, C), dt)
+        self.ops.aligned_sample(warped, affine, ks, out)
+        return out
+
+    # ---- RAP module (RefVSR.py:123-149) --------------------------------------------------------------
+    def _rap(self, lr, ref8, conf, conf_prop, idx, feat_prop, feat_prop_UP, ref_feat_down, ref_feat, tag):
+        C, dt = self.mid_channels, self.act_dtype
+        h, w = conf.shape
+        # level 1: aa1 (scale 1, align=False) is a pure gather (attention.py:142-144)
+        aligned = self._buf('rap.al1', (h, w, C), dt)
+        self.ops.gather_blocks(ref_feat_down, idx, h, w, 1, aligned)
+        cp8 = self._buf('rap.cp8', (h, w, 8), dt)
+        self.ops.conf_pair(conf_prop, conf, cp8, up2=False)
+        a0 = self._conv('conf_fusion.0.0', cp8, None, self._buf('rap.a0', (h, w, 16), dt), [(2, 8)], act_pre=ACT_LRELU02)
+        alpha = self._conv('conf_fusion.1.0', a0, None, self._buf('rap.alpha', (h, w, C), dt), [(16, 16)], act_pre=ACT_LRELU02)
+        f0 = self._conv('feat_fusion.0.0', feat_prop, aligned, self._buf('rap.f0', (h, w, C), dt), [(C, C), (C, C)],
+                        act_pre=ACT_LRELU02)
+        fused = self._conv('feat_fusion.1.0', f0, None, self._buf('rap.fused', (h, w, C), dt), [(C, C)],
+                           act_pre=ACT_LRELU02, gate=alpha, res=feat_prop)
+        feat_out = self._buf(tag + '.feat', (h, w, C), dt)
+        self._reslist('feat_decoder', 8, fused, feat_out, 'rap.dec1')
+
+        # level 2
+        aligned_up = self._aa2(lr, ref8, idx, ref_feat, h, w)
+        up = self._conv('upsample1.upsample_conv', feat_out, None, self._buf('rap.up', (2 * h, 2 * w, C), dt), [(C, C)],
+                        pixel_shuffle=True)
+        fu = self._conv('feat_fusion2_1.0.0', feat_prop_UP, up, self._buf('rap.fu', (2 * h, 2 * w, C), dt),
+                        [(C, C), (C, C)], act_pre=ACT_LRELU02)
+        cp8u = self._buf('rap.cp8u', (2 * h, 2 * w, 8), dt)
+        self.ops.conf_pair(conf_prop, conf, cp8u, up2=True)
+        b0 = self._conv('conf_fusion2.0.0', cp8u, None, self._buf('rap.b0', (2 * h, 2 * w, 16), dt), [(2, 8)], act_pre=ACT_LRELU02)
+        alpha2 = self._conv('conf_fusion2.1.0', b0, None, self._buf('rap.alpha2', (2 * h, 2 * w, C), dt), [(16, 16)],
+                            act_pre=ACT_LRELU02)
+        g0 = self._conv('feat_fusion2.0.0', fu, aligned_up, self._buf('rap.g0', (2 * h, 2 * w, C), dt), [(C, C), (C, C)],
+                        act_pre=ACT_LRELU02)
+        fused2 = self._conv('feat_fusion2.1.0', g0, None, self._buf('rap.fused2', (2 * h, 2 * w, C), dt), [(C, C)],
+                            act_pre=ACT_LRELU02, gate=alpha2, res=fu)
+        feat_up_out = self._buf(tag + '.featUP', (2 * h, 2 * w, C), dt)
+        self._reslist('feat_decoder2', 4, fused2, feat_up_out, 'rap.dec2')
+        conf_out = self._buf(tag + '.conf', (h, w), torch.float32)
+        self.ops.conf_max(conf_prop, conf, conf_out)
+        return feat_out, feat_up_out, conf_out
+
+    # ---- upsampling tail (RefVSR.py:104-119,288,297) -------------------------------------------------
+    def _compute_up(self, bw_up, fw_up, conf_bw, conf_fw, lr_center, clamp01):
+        C, dt = self.mid_channels, self.act_dtype
+        H2, W2 = bw_up.shape[0], bw_up.shape[1]
+        h, w = H2 // 2, W2 // 2
+        cp8 = self._buf('up.cp8', (H2, W2, 8), dt)
+        self.ops.conf_pair(conf_bw, conf_fw, cp8, up2=True)
+        base = self._conv('fusion_UP', bw_up, fw_up, self._buf('up.base', (H2, W2, C), dt), [(C, C), (C, C)], pad=0)
+        a0 = self._conv('conf_fusion_BWFW.0.0', cp8, None, self._buf('up.a0', (H2, W2, 16), dt), [(2, 8)], act_pre=ACT_LRELU02)
+        alpha = self._conv('conf_fusion_BWFW.1.0', a0, None, self._buf('up.alpha', (H2, W2, C), dt), [(16, 16)],
+                           act_pre=ACT_LRELU02)
+        f0 = self._conv('feat_fusion_BWFW.0.0', bw_up, fw_up, self._buf('up.f0', (H2, W2, C), dt), [(C, C), (C, C)],
+                        act_pre=ACT_LRELU02)
+        fused = self._conv('feat_fusion_BWFW.1.0', f0, None, self._buf('up.fused', (H2, W2, C), dt), [(C, C)],
+                           act_pre=ACT_LRELU02, gate=alpha, res=base)
+        dec = self._reslist('feat_decoder_BWFW', 4, fused, self._buf('up.dec', (H2, W2, C), dt), 'up.decs')
+        # lrelu(pixel_shuffle(conv)) == pixel_shuffle(lrelu(conv))  (RefVSR.py:114-115)
+        hr = self._conv('upsample2.upsample_conv', dec, None, self._buf('up.hr', (4 * h, 4 * w, C), dt), [(C, C)],
+                        act_pre=ACT_LRELU01, pixel_shuffle=True)
+        hr2 = self._conv('conv_hr', hr, None, self._buf('up.hr2', (4 * h, 4 * w, C), dt), [(C, C)], act_pre=ACT_LRELU01)
+        last = self._conv('conv_last', hr2, None, self._buf('up.last', (4 * h, 4 * w, 4), torch.float32), [(C, C)])
+        out = torch.empty((3, 4 * h, 4 * w), dtype=torch.float32, device=self._device)
+        self.ops.reconstruct(last, lr_center, self.scale, clamp01, out)
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # per-frame products with exact reuse across sliding windows
+    # ------------------------------------------------------------------------------------------
+    def _frame_products(self, st, lrs, refs, a0, t, need_match_from):
+        """Make sure the per-frame caches hold what this window needs.  Frames are addressed by their
+        absolute index a = a0 + j (a0 = number of calls since the stream started)."""
+        pyr = st['pyr']
+        for k in [k for k in pyr if k < a0]:
+            del pyr[k]
+        for name in ('fw', 'bw', 'match', 'reff'):
+            d = st[name]
+            for k in [k for k in d if k < a0]:
+                del d[k]
+
+        def pyramid(j):
+            if a0 + j not in pyr:
+                pyr[a0 + j] = self._pyramid(lrs[j])
+            return pyr[a0 + j]
+
+        h, w = lrs.shape[2], lrs.shape[3]
+        ev = _cget(self.config, 'EVAL', None)
+        zero_flow = bool(_cget(ev, 'is_gradio', False)) if ev is not None else False   # RefVSR.py:183-191
+        for j in st['need_fw']:          # forward_flows[j] = Flow(lrs[j+1], lrs[j])   (RefVSR.py:182-184)
+            if a0 + j not in st['fw']:
+                st['fw'][a0 + j] = (torch.zeros((h, w, 2), dtype=torch.float32, device=self._device) if zero_flow
+                                    else self._spynet(pyramid(j + 1), pyramid(j), h, w))
+        for j in st['need_bw']:          # backward_flows[j] = Flow(lrs[j], lrs[j+1])  (RefVSR.py:187-189)
+            if a0 + j not in st['bw']:
+                st['bw'][a0 + j] = (torch.zeros((h, w, 2), dtype=torch.float32, device=self._device) if zero_flow
+                                    else self._spynet(pyramid(j), pyramid(j + 1), h, w))
+        for j in range(need_match_from, t):
+            if a0 + j not in st['match']:
+                st['match'][a0 + j] = self._feature_match(lrs[j], refs[j])     # RefVSR.py:196-204
+            if a0 + j not in st['reff']:
+                st['reff'][a0 + j] = self._ref_features(refs[j])
+
+    # ------------------------------------------------------------------------------------------
+    # forward (RefVSR.py:151-325)
+    # ------------------------------------------------------------------------------------------
+    def forward(self, lrs, refs, is_first_frame, is_log=False, is_train=False):
+        outs = collections.OrderedDict()
+        if is_log:
+            outs['vis'] = collections.OrderedDict()
+        if lrs.dim() != 5 or refs.dim() != 5:
+            raise ValueError('lrs / refs must be (n, t, c, h, w)')
+        n, t, c, h, w = lrs.size()
+        if c != 3 or refs.size(2) != 3 or refs.size(1) != t or refs.size(0) != n:
+            raise ValueError(f'unexpected input shapes {tuple(lrs.shape)} / {tuple(refs.shape)}')
+        if refs.size(3) % 2 or refs.size(4) % 2:
+            raise ValueError('reference frames must have even height/width (2x2 avg-pool and 2x2 block '
+                             'gather, attention.py:51,142-144; odd sizes take the reference\'s reflection-'
+                             'padded unfold path, which is not implemented)')
+        self._device = lrs.device
+
+        caller_first = bool(is_first_frame)
+        if not is_train:                                                     # RefVSR.py:168-170
+            if self.max_frame_itr_num is not None and self.frame_itr_num == self.max_frame_itr_num:
+                is_first_frame = True
+
+        with torch.no_grad():
+            results, vis = [], None
+            for b in range(n):
+                res_b, vis_b = self._forward_one(b, lrs[b].float().contiguous(), refs[b].float().contiguous(),
+                                                 bool(is_first_frame), caller_first, bool(is_log), bool(is_train))
+                results.append(res_b)
+                vis = vis_b if vis is None else vis
+            out = torch.stack(results, 0)
+
+        if not is_train:                                                     # RefVSR.py:292-297
+            if is_first_frame:
+                self.frame_itr_num = 0
+            self.frame_itr_num += 1
+        outs['result'] = out
+        if is_log and vis is not None:
+            outs['vis'].update(vis.get('vis', {}))
+            if _cget(self.config, 'save_sample', False) and 'eval_vis' in vis:
+                outs['eval_vis'] = vis['eval_vis']
+        return outs
+
+    def _forward_one(self, b, lrs, refs, is_first_frame, caller_first, is_log, is_train):
+        ops = self.ops
+        C, dt = self.mid_channels, self.act_dtype
+        t, _, h, w = lrs.shape
+        mid = t // 2
+
+        # stream bookkeeping for exact reuse: a caller-declared first frame starts a new stream; forced
+        # resets (reset_branch) keep sliding, so the caches stay valid across them.
+        st = self._state.get(b)
+        if st is None or caller_first or not self.reuse or is_train or st.get('shape') != (t, h, w, refs.shape[2], refs.shape[3]):
+            st = {'a0': 0, 'pyr': {}, 'fw': {}, 'bw': {}, 'match': {}, 'reff': {}, 'prev': st.get('prev') if st else None,
+                  'shape': (t, h, w, refs.shape[2], refs.shape[3])}
+            self._state[b] = st
+        else:
+            st['a0'] += 1
+        a0 = st['a0']
+
+        if is_first_frame:
+            range_start = 0
+        else:
+            range_start = mid if not is_train else 0                          # RefVSR.py:173-176
+            if st['prev'] is None:
+                raise RuntimeError('is_first_frame=False but no propagated state exists '
+                                   '(the reference fails the same way: RefVSR.py:256-260)')
+        # flows actually consumed by this call (the reference computes all 2(t-1), RefVSR.py:179-193)
+        st['need_bw'] = list(range(mid, t - 1))
+        st['need_fw'] = sorted(set(range(range_start, mid)) | ({mid} if mid < t - 1 else set()))
+        self._frame_products(st, lrs, refs, a0, t, range_start)
+
+        lr8 = {}
+
+        def lr_nhwc(i):
+            if i not in lr8:
+                x = torch.empty((h, w, 8), dtype=dt, device=self._device)
+                ops.prep_image(lrs[i], x)
+                lr8[i] = x
+            return lr8[i]
+
+        vis = {'vis': collections.OrderedDict()} if is_log else None
+
+        # ---------------- backward branch (RefVSR.py:211-238) ----------------
+        feat_prop = self._buf('bw.z.feat', (h, w, C), dt).zero_()
+        feat_prop_UP = self._buf('bw.z.featUP', (2 * h, 2 * w, C), dt).zero_()
+        conf_prop = self._buf('bw.z.conf', (h, w), torch.float32).zero_()
+        for i in range(t - 1, mid - 1, -1):
+            if i < t - 1:
+                flow = st['bw'][a0 + i]
+                wf = self._buf('bw.w.feat', (h, w, C), dt)
+                ops.warp(feat_prop, flow, wf)
+                wc = self._buf('bw.w.conf', (h, w), torch.float32)
+                ops.warp(conf_prop, flow, wc)
+                wu = self._buf('bw.w.featUP', (2 * h, 2 * w, C), dt)
+                ops.warp(feat_prop_UP, flow, wu, flow_up2=True)                # RefVSR.py:220
+                feat_prop, conf_prop, feat_prop_UP = wf, wc, wu
+                if is_log and i == mid:
+                    vis['vis']['BW_LR_next_warp'] = self._warp_image(lrs[i + 1], flow)
+            agg = self._prop_resblocks('backward_resblocks', lr_nhwc(i), feat_prop,
+                                       self._buf('bw.agg', (h, w, C), dt), 'bw.rb')
+            conf, idx = st['match'][a0 + i]
+            ref8, ref_feat, ref_feat_down = st['reff'][a0 + i]
+            feat_prop, feat_prop_UP, conf_prop = self._rap(lrs[i], ref8, conf, conf_prop, idx, agg, feat_prop_UP,
+                                                           ref_feat_down, ref_feat, f'bw.rap{i % 2}')
+        backward_feat_UP, conf_bw = feat_prop_UP, conf_prop
+        # (the forward branch writes 'fw.*' buffers only, so these stay intact)
+
+        # ---------------- forward branch (RefVSR.py:241-283) ----------------
+        if is_first_frame:
+            feat_prop = self._buf('fw.z.feat', (h, w, C), dt).zero_()
+            feat_prop_UP = self._buf('fw.z.featUP', (2 * h, 2 * w, C), dt).zero_()
+            conf_prop = self._buf('fw.z.conf', (h, w), torch.float32).zero_()
+            range_start = 0
+        flow = None
+        for i in range(range_start, mid + 1):
+            if i > range_start:
+                flow = st['fw'][a0 + i - 1]
+                wf = self._buf('fw.w.feat', (h, w, C), dt)
+                ops.warp(feat_prop, flow, wf)
+                # quirk kept on purpose: the LR-resolution feat_prop (already warped once) is warped onto
+                # the 2x grid, the propagated feat_prop_UP is dropped (RefVSR.py:252-254)
+                wu = self._buf('fw.w.featUP', (2 * h, 2 * w, C), dt)
+                ops.warp(wf, flow, wu, flow_up2=True)
+                wc = self._buf('fw.w.conf', (h, w), torch.float32)
+                ops.warp(conf_prop, flow, wc)
+                feat_prop, feat_prop_UP, conf_prop = wf, wu, wc
+            elif i == range_start and not is_first_frame:
+                prev = st['prev']
+                flow = prev['flow']
+                wf = self._buf('fw.w.feat', (h, w, C), dt)
+                ops.warp(prev['feat'], flow, wf)
+                wu = self._buf('fw.w.featUP', (2 * h, 2 * w, C), dt)
+                ops.warp(prev['featUP'], flow, wu, flow_up2=True)              # RefVSR.py:259
+                wc = self._buf('fw.w.conf', (h, w), torch.float32)
+                ops.warp(prev['conf'], flow, wc)
+                feat_prop, feat_prop_UP, conf_prop = wf, wu, wc
+            if is_log and i == mid and flow is not None:
+                vis['vis']['FW_LR_prev_warp'] = self._warp_image(lrs[i - 1], flow)
+            agg = self._prop_resblocks('forward_resblocks', lr_nhwc(i), feat_prop,
+                                       self._buf('fw.agg', (h, w, C), dt), 'fw.rb')
+            conf, idx = st['match'][a0 + i]
+            ref8, ref_feat, ref_feat_down = st['reff'][a0 + i]
+            feat_prop, feat_prop_UP, conf_prop = self._rap(lrs[i], ref8, conf, conf_prop, idx, agg, feat_prop_UP,
+                                                           ref_feat_down, ref_feat, f'fw.rap{i % 2}')
+            if (is_train and i == 0) or (not is_train and i == mid):           # RefVSR.py:279-283
+                st['prev'] = {'feat': feat_prop.clone(), 'featUP': feat_prop_UP.clone(), 'conf': conf_prop.clone(),
+                              'flow': st['fw'][a0 + i].clone() if (a0 + i) in st['fw'] else None}
+
+        # ---------------- U (RefVSR.py:286-297) ----------------
+        out = self._compute_up(backward_feat_UP, feat_prop_UP, conf_bw, conf_prop, lrs[mid], clamp01=not is_train)
+
+        if is_log and _cget(self.config, 'save_sample', False):
+            ev = collections.OrderedDict()
+            ev['conf_map'] = st['match'][a0 + mid][0].view(1, 1, h, w).clone()
+            ev['conf_map_prop_backward'] = conf_bw.view(1, 1, h, w).clone()
+            ev['conf_map_prop_forward'] = conf_prop.view(1, 1, h, w).clone()
+            ev['conf_map_prop'] = torch.maximum(ev['conf_map_prop_backward'], ev['conf_map_prop_forward'])
+            vis['eval_vis'] = ev
+        return out, vis
+
+    def _warp_image(self, img, flow):
+        """debug visualisation `warp(lrs[:, i±1], flow)` (RefVSR.py:222,263) -> (1,3,h,w)"""
+        x = img.permute(1, 2, 0).contiguous()
+        o = torch.empty_like(x)
+        self.ops.warp(x, flow, o)
+        return o.permute(2, 0, 1).unsqueeze(0).contiguous()

@@ -1,0 +1,118 @@
+"""Weight repacking: nn.Conv2d parameters (cout, cin, kh, kw) -> the layouts rv_conv2d consumes.
+
+Two layouts (see include/refvsr_b200.h):
+  * SIMT : fp32 [K][ceil4(cout)],  k = (ky*kw + kx)*(alloc0+alloc1) + c   (c over the *allocated*
+           channels of src0 then src1; padding channels get zero weights)
+  * TC   : 16-bit [nblk][S][kh][NB][64], S = kw * (chunks0 + chunks1), stage s = kx*nchunks + chunk;
+           every [NB][64] slab is the byte image of a K-major SWIZZLE_128B UMMA operand tile
+           (16-byte chunk j of row r stored at chunk j ^ (r % 8)), so the kernel fetches it with a plain
+           bulk copy and hands it to tcgen05.mma unchanged.
+"""
+from dataclasses import dataclass
+
+import torch
+
+from .lib import IMPL_SIMT, IMPL_TC
+
+
+@dataclass
+class PackedConv:
+    name: str
+    cout: int
+    kh: int
+    kw: int
+    stride: int
+    pad: int
+    alloc0: int
+    alloc1: int
+    impl: int
+    nb: int
+    k_real: int
+    wpack: torch.Tensor
+    bias: torch.Tensor
+
+
+def _expand_inputs(weight, srcs):
+    """weight (cout, sum(real), kh, kw) -> (cout, sum(alloc), kh, kw) with zero columns for padding."""
+    cout, cin, kh, kw = weight.shape
+    assert cin == sum(r for r, _ in srcs), f'weight has {cin} input channels, sources give {srcs}'
+    parts, o = [], 0
+    for real, alloc in srcs:
+        w = weight[:, o:o + real]
+        if alloc > real:
+            w = torch.cat([w, weight.new_zeros(cout, alloc - real, kh, kw)], 1)
+        parts.append(w)
+        o += real
+    return torch.cat(parts, 1)
+
+
+def pack_simt(weight, srcs):
+    w = _expand_inputs(weight.float(), srcs)            # (cout, ct, kh, kw)
+    cout, ct, kh, kw = w.shape
+    ldw = (cout + 3) // 4 * 4
+    wk = w.permute(2, 3, 1, 0).reshape(kh * kw * ct, cout)  # k = (ky*kw+kx)*ct + c
+    out = w.new_zeros(kh * kw * ct, ldw)
+    out[:, :cout] = wk
+    return out.contiguous()
+
+
+def choose_nb(cout):
+    """output channels per CTA column block for the TC kernel (multiple of 16, <= 96 so that 3x3
+    weights of a two-source conv stay resident in shared memory)."""
+    c16 = (cout + 15) // 16 * 16
+    if c16 <= 96:
+        return c16
+    for nb in (96, 80, 64, 48, 32, 16):
+        if c16 % nb == 0:
+            return nb
+    return 64
+
+
+def pack_tc(weight, srcs, dtype, nb):
+    cout, _, kh, kw = weight.shape
+    w = weight.float()
+    nblk = (cout + nb - 1) // nb
+    # split input channels into 64-wide chunks per source
+    chunks = []      # (weight slice (cout, <=64 real-or-pad, kh, kw))
+    o = 0
+    for real, alloc in srcs:
+        ws = w[:, o:o + real]
+        o += real
+        nch = (alloc + 63) // 64
+        for j in range(nch):
+            sl = ws[:, 64 * j: min(64 * j + 64, real)] if 64 * j < real else ws[:, :0]
+            pad = 64 - sl.shape[1]
+            if pad:
+                sl = torch.cat([sl, w.new_zeros(cout, pad, kh, kw)], 1)
+            chunks.append(sl)
+    nchunks = len(chunks)
+    S = kw * nchunks
+    wc = torch.stack(chunks, 0)                               # (nchunks, cout, 64, kh, kw)
+    wpad = w.new_zeros(nchunks, nblk * nb, 64, kh, kw)
+    wpad[:, :cout] = wc
+    # -> [nblk][kx][chunk][ky][n][c]
+    t = wpad.view(nchunks, nblk, nb, 64, kh, kw).permute(1, 5, 0, 4, 2, 3).contiguous()
+    t = t.view(nblk, S, kh, nb, 8, 8)                         # 64 channels = 8 chunks x 8 elements
+    out = torch.empty_like(t)
+    ar = torch.arange(8, device=t.device)
+    for m in range(8):
+        out[:, :, :, m::8] = t[:, :, :, m::8][..., ar ^ m, :]
+    return out.view(nblk, S, kh, nb, 64).to(dtype).contiguous()
+
+
+def pack_conv(name, weight, bias, srcs, stride, pad, act_dtype, device, prefer_tc=True, bias_add=0.0):
+    """Pick the implementation and build the packed tensors.  `srcs` = [(real, alloc), ...] (1 or 2)."""
+    cout, _, kh, kw = weight.shape
+    alloc0 = srcs[0][1]
+    alloc1 = srcs[1][1] if len(srcs) > 1 else 0
+    tc_ok = (prefer_tc and stride == 1 and act_dtype in (torch.float16, torch.bfloat16)
+             and all(a % 8 == 0 for _, a in srcs) and kh <= 7 and kw <= 7)
+    b = bias.detach().float() + bias_add
+    if tc_ok:
+        nb = choose_nb(cout)
+        wp = pack_tc(weight.detach(), srcs, act_dtype, nb).to(device)
+        return PackedConv(name, cout, kh, kw, stride, pad, alloc0, alloc1, IMPL_TC, nb,
+                          kh * kw * (alloc0 + alloc1), wp, b.to(device).contiguous())
+    wp = pack_simt(weight.detach(), srcs).to(device)
+    return PackedConv(name, cout, kh, kw, stride, pad, alloc0, alloc1, IMPL_SIMT, 0,
+                      kh * kw * (alloc0 + alloc1), wp, b.to(device).contiguous())
