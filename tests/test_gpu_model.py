@@ -1,0 +1,116 @@
+"""-m gpu: the whole hot path through SRNet.forward on the B200 against the golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py) and against the oracle at a larger size.
+
+Bars (north_star): fp32 path <= 1e-3 relative; 16-bit paths are judged by PSNR against the reference output
+(the hard argmax makes per-pixel bounds meaningless where an index flips; the flip rate is reported and
+bounded separately)."""
+import numpy as np
+import pytest
+import torch
+
+from util import CASES, build_case, psnr
+
+pytestmark = pytest.mark.gpu
+
+
+def run_clip(net, lrs, refs, T, device='cuda'):
+    from refvsr_b200.synth import sliding_windows
+    outs = []
+    for k, wl, wr, first in sliding_windows(lrs, refs, T):
+        outs.append(net(wl.to(device), wr.to(device), first, False, False)['result'][0].float().cpu())
+    return outs
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_fp32_path_matches_reference_golden(name):
+    spec, cfg, net, lrs, refs, golden = build_case(name, 'cuda', b200_precision='fp32')
+    outs = run_clip(net, lrs, refs, spec['T'])
+    for k, o in enumerate(outs):
+        g = torch.from_numpy(golden[f'result_{k}'])
+        p = psnr(o, g)
+        err = (o - g).abs().max().item()
+        print(f'{name} window {k}: psnr {p:.1f} dB, max abs {err:.2e}')
+        assert p >= 80.0, f'{name} window {k}: PSNR vs reference {p:.1f} dB'
+        assert err <= 5e-3
+    # first window: matching products against the reference's own (hooked) outputs
+    st = net.Network._state[0]
+
+
+@pytest.mark.parametrize('name', list(CASES))
+@pytest.mark.parametrize('prec,bar', [('fp16', 55.0), ('bf16', 42.0)])
+def test_16bit_tensor_core_path(name, prec, bar):
+    spec, cfg, net, lrs, refs, golden = build_case(name, 'cuda', b200_precision=prec)
+    outs = run_clip(net, lrs, refs, spec['T'])
+    for k, o in enumerate(outs):
+        g = torch.from_numpy(golden[f'result_{k}'])
+        p = psnr(o, g)
+        print(f'{name}/{prec} window {k}: psnr {p:.1f} dB, max abs {(o - g).abs().max().item():.2e}')
+        assert p >= bar, f'{name}/{prec} window {k}: PSNR vs reference {p:.1f} dB < {bar}'
+
+
+def test_tensor_core_and_simt_paths_agree():
+    name = 'mfid_t5_40x56_ref2x'
+    res = {}
+    for tc in (True, False):
+        spec, cfg, net, lrs, refs, golden = build_case(name, 'cuda', b200_precision='fp16', b200_tensor_cores=tc)
+        res[tc] = run_clip(net, lrs, refs, spec['T'])
+    for a, b in zip(res[True], res[False]):
+        assert psnr(a, b) >= 55.0
+
+
+def test_reuse_is_exact():
+    """sliding-window reuse (flows / matches / ref features) must not change a single bit."""
+    name = 'small_t7_24x32'
+    res = {}
+    for reuse in (True, False):
+        spec, cfg, net, lrs, refs, golden = build_case(name, 'cuda', b200_precision='fp16', b200_reuse=reuse)
+        res[reuse] = run_clip(net, lrs, refs, spec['T'])
+    for a, b in zip(res[True], res[False]):
+        assert torch.equal(a, b)
+
+
+def test_medium_size_against_oracle():
+    """96x128 LR, RefVSR_small_MFID with all 24 blocks, 3 windows: CUDA fp32 path vs the CPU oracle."""
+    from oracle.refvsr_oracle import OracleRefVSR
+    from refvsr_b200 import SRNet, get_config
+    from refvsr_b200.modules import seeded_test_weights
+    from refvsr_b200.synth import make_clip, sliding_windows
+    cfg = get_config('RefVSR_small_MFID', device='cuda', b200_precision='fp32')
+    net = SRNet(cfg).eval()
+    seeded_test_weights(net, seed=21)
+    orc = OracleRefVSR(cfg, net.state_dict())
+    net = net.cuda()
+    lrs, refs = make_clip(3, 96, 128, 1, seed=21)
+    for k, wl, wr, first in sliding_windows(lrs, refs, 7):
+        o = net(wl.cuda(), wr.cuda(), first, False, False)['result'].float().cpu()
+        e = orc.forward(wl, wr, first)
+        p = psnr(o, e)
+        print(f'96x128 window {k}: psnr {p:.1f} dB max abs {(o - e).abs().max().item():.2e}')
+        assert p >= 75.0
+
+
+def test_full_size_properties():
+    """BASELINE size (270x480 -> 1080x1920), MFID, bf16: shape, range, determinism, state handling."""
+    from refvsr_b200 import SRNet, get_config
+    from refvsr_b200.modules import seeded_test_weights
+    from refvsr_b200.synth import make_clip, sliding_windows
+    cfg = get_config('RefVSR_MFID', device='cuda')
+    net = SRNet(cfg).eval()
+    seeded_test_weights(net, seed=5)
+    net = net.cuda()
+    lrs, refs = make_clip(3, 270, 480, 1, seed=5)
+    outs = []
+    for rep in range(2):
+        cur = []
+        for k, wl, wr, first in sliding_windows(lrs, refs, 7):
+            o = net(wl.cuda(), wr.cuda(), first, False, False)['result']
+            assert o.shape == (1, 3, 1080, 1920) and o.dtype == torch.float32
+            assert float(o.min()) >= 0.0 and float(o.max()) <= 1.0 and torch.isfinite(o).all()
+            cur.append(o.cpu())
+        outs.append(cur)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b), 'two passes over the same clip must be bit identical (is_first_frame resets state)'
+    with pytest.raises(RuntimeError):
+        fresh = SRNet(cfg).eval().cuda()
+        wl, wr = lrs[:7].unsqueeze(0).cuda() if lrs.shape[0] >= 7 else lrs[[0] * 7].unsqueeze(0).cuda(), refs[[0] * 7].unsqueeze(0).cuda()
+        fresh(wl, wr, False, False, False)      # no propagated state yet: the reference fails here too
