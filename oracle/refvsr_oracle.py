@@ -254,6 +254,7 @@ class OracleRefVSR:
         self.max_frame_itr_num = config.reset_branch
         self.prev = None
         self.trace = None            # set to a dict to record intermediates
+        self.compute_all_flows = False   # True: also compute the flows the reference computes but never uses
 
     # ---- layers ----
     def conv(self, name, x, stride=1, pad=None):
@@ -388,6 +389,12 @@ class OracleRefVSR:
             fw[j] = lrs.new_zeros(n, 2, h, w) if gradio else self.spynet(lrs[:, j + 1], lrs[:, j])
         for j in range(mid, t - 1):
             bw[j] = lrs.new_zeros(n, 2, h, w) if gradio else self.spynet(lrs[:, j], lrs[:, j + 1])
+        if self.compute_all_flows and not gradio:   # cost model of the reference as written (RefVSR.py:179-193)
+            for j in range(0, t - 1):
+                if j not in fw:
+                    self.spynet(lrs[:, j + 1], lrs[:, j])
+                if j not in bw:
+                    self.spynet(lrs[:, j], lrs[:, j + 1])
         conf_maps, index_maps = {}, {}
         for i in range(range_start, t):                                   # RefVSR.py:196-204
             conf_maps[i], index_maps[i] = self.feature_match(lrs[:, i], refs[:, i])

@@ -1,0 +1,68 @@
+"""Weight repacking (refvsr_b200/packing.py): the SIMT matrix and the swizzled tcgen05 image decode back to
+the original convolution weights under the layouts documented in include/refvsr_b200.h / conv_tc.cu."""
+import pytest
+import torch
+
+from refvsr_b200 import packing
+
+
+def unswizzle_tc(wp, srcs, cout, kh, kw, nb):
+    """inverse of pack_tc following the kernel's addressing: stage s = kx*nchunks + chunk; row r of a
+    [NB][64] slab holds 16-byte chunk j at position j ^ (r % 8)."""
+    nblk, S, _, _, _ = wp.shape
+    allocs = [a for _, a in srcs]
+    nch = [(a + 63) // 64 for a in allocs]
+    nchunks = sum(nch)
+    w = torch.zeros(cout, sum(allocs), kh, kw)
+    t = wp.float().view(nblk, S, kh, nb, 8, 8)
+    for b in range(nblk):
+        for s in range(S):
+            kx, ch = divmod(s, nchunks)
+            src, cj = (0, ch) if ch < nch[0] else (1, ch - nch[0])
+            base = (0 if src == 0 else allocs[0]) + 64 * cj
+            for r in range(nb):
+                n = b * nb + r
+                if n >= cout:
+                    continue
+                row = torch.stack([t[b, s, :, r, j ^ (r % 8), :] for j in range(8)], 1).reshape(kh, 64)
+                width = min(64, allocs[src] - 64 * cj)
+                w[n, base:base + width, :, kx] = row[:, :width].t()
+    return w
+
+
+@pytest.mark.parametrize('srcs,cout,k', [([(48, 48)], 48, 3), ([(3, 8), (48, 48)], 48, 3), ([(64, 64)], 32, 7),
+                                         ([(48, 48)], 192, 3), ([(16, 16)], 2, 7), ([(48, 48), (48, 48)], 48, 1),
+                                         ([(96, 96)], 24, 3)])
+def test_pack_tc_roundtrip(srcs, cout, k):
+    cin = sum(r for r, _ in srcs)
+    w = torch.randn(cout, cin, k, k).half().float()
+    nb = packing.choose_nb(cout)
+    assert nb % 16 == 0 and 16 <= nb <= 256
+    wp = packing.pack_tc(w, srcs, torch.float16, nb)
+    nchunks = sum((a + 63) // 64 for _, a in srcs)
+    assert wp.shape == ((cout + nb - 1) // nb, k * nchunks, k, nb, 64)
+    back = unswizzle_tc(wp, srcs, cout, k, k, nb)
+    exp = packing._expand_inputs(w, srcs)
+    assert torch.equal(back, exp)
+
+
+def test_pack_simt_layout():
+    srcs = [(3, 8), (5, 8)]
+    w = torch.randn(6, 8, 3, 3)
+    m = packing.pack_simt(w, srcs)
+    assert m.shape == (3 * 3 * 16, 8)
+    ct = 16
+    for (n, c_real, c_alloc, ky, kx) in [(0, 0, 0, 0, 0), (5, 2, 2, 1, 2), (3, 4, 9, 2, 1), (2, 7, 12, 0, 1)]:
+        assert m[(ky * 3 + kx) * ct + c_alloc, n] == w[n, c_real, ky, kx]
+    assert m[(0 * 3 + 0) * ct + 5, 0] == 0 and m[:, 6:].abs().sum() == 0     # padding channels / columns
+
+
+def test_pack_conv_chooses_impl():
+    w, b = torch.randn(48, 48, 3, 3), torch.zeros(48)
+    from refvsr_b200.lib import IMPL_SIMT, IMPL_TC
+    assert packing.pack_conv('a', w, b, [(48, 48)], 1, 1, torch.float16, 'cpu', True).impl == IMPL_TC
+    assert packing.pack_conv('a', w, b, [(48, 48)], 2, 1, torch.float16, 'cpu', True).impl == IMPL_SIMT
+    assert packing.pack_conv('a', w, b, [(48, 48)], 1, 1, torch.float32, 'cpu', True).impl == IMPL_SIMT
+    assert packing.pack_conv('a', w, b, [(48, 48)], 1, 1, torch.float16, 'cpu', False).impl == IMPL_SIMT
+    p = packing.pack_conv('a', w, b, [(48, 48)], 1, 1, torch.float16, 'cpu', True, bias_add=1.0)
+    assert torch.equal(p.bias, torch.ones(48))
