@@ -26,9 +26,11 @@ int fail(int code, const char* fmt, ...);
 #define RV_CUDA_OK(expr)                                                                  \
   do {                                                                                    \
     cudaError_t _e = (expr);                                                              \
-    if (_e != cudaSuccess)                                                                \
+    if (_e != cudaSuccess) {                                                              \
+      (void)cudaGetLastError(); /* do not leave a sticky error for the next launch */     \
       return rv::fail(RV_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
                       __FILE__, __LINE__);                                                \
+    }                                                                                     \
   } while (0)
 
 // call after every kernel launch

@@ -305,10 +305,10 @@ template <typename TI, typename TR, typename TO>
 static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& p, dim3 grid, size_t smem,
                      cudaStream_t st) {
   auto kern = conv_tc_kernel<TI, TR, TO>;
-  static size_t configured = 0;
+  static size_t configured = 0;   // per template instantiation
   if (smem > configured) {
-    RV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    configured = g_max_smem;
+    RV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
   }
   kern<<<grid, 192, smem, st>>>(tm0, tm1, p);
   RV_LAUNCH_CHECK("conv_tc");
@@ -344,7 +344,7 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   p.w_bytes = (uint32_t)d->kh * p.NB * 128;
   const int nblk = (d->cout + p.NB - 1) / p.NB;
   // shared-memory plan: weights resident when they leave room for >= 3 A slots
-  const size_t budget = (size_t)g_max_smem - 1024 /*alignment*/ - 2048 /*static*/;
+  const size_t budget = (size_t)g_max_smem - 1024 /*alignment*/ - 4096 /*static: barriers, bias*/;
   const size_t w_all = (size_t)p.S * p.w_bytes;
   if (w_all + 3 * (size_t)p.a_bytes <= budget) {
     p.resident = 1;

@@ -233,7 +233,7 @@ static int match_tc(const void* A, int P, const void* B, int R, int kpad, float 
   p.P = P; p.R = R; p.nk = kpad / 64; p.ntiles_n = (R + MT_BN - 1) / MT_BN;
   p.out_scale = out_scale; p.conf = conf; p.idx = idx;
   const size_t a_bytes = (size_t)p.nk * MT_BM * 128;
-  const size_t budget = (size_t)max_smem - 1024 - 1024;
+  const size_t budget = (size_t)max_smem - 1024 - 2048;
   p.slots = (int)std::min<size_t>(MT_SLOTS_MAX, (budget - a_bytes) / ((size_t)MT_BN * 128));
   RV_REQUIRE(p.slots >= 2, "rv_match_argmax(tc): not enough shared memory");
   const size_t smem = 1024 + a_bytes + (size_t)p.slots * MT_BN * 128;
@@ -242,10 +242,10 @@ static int match_tc(const void* A, int P, const void* B, int R, int kpad, float 
   if (rc) return rc;
   rc = make_rows_tmap(&tmB, B, kpad, R, MT_BN);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    RV_CUDA_OK(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    configured = true;
+  static size_t configured = 0;
+  if (smem > configured) {
+    RV_CUDA_OK(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
   }
   match_tc_kernel<<<cdiv(P, MT_BM), 192, smem, st>>>(tmA, tmB, p);
   RV_LAUNCH_CHECK("match_tc");
