@@ -88,6 +88,12 @@ def make_model(workload, precision, device):
     return cfg, net.to(device)
 
 
+def host_threads():
+    """threads for the CPU legs: all cores up to 16 - beyond that the oracle's many small ATen ops lose to
+    oversubscription (measured on the 128-core GPU host: 128 threads were >10x slower than 8)."""
+    return int(os.environ.get('REFVSR_CPU_THREADS', min(os.cpu_count() or 1, 16)))
+
+
 def window_indices(k, n):
     return [min(max(k - T // 2 + j, 0), n - 1) for j in range(T)]      # data_loader/datasets.py:233-234
 
@@ -167,7 +173,7 @@ def cpu_baseline_sample(workload, threads=None):
     from refvsr_b200 import SRNet, get_config
     from refvsr_b200.modules import seeded_test_weights
     from refvsr_b200.synth import make_clip
-    cores = threads or os.cpu_count() or 1
+    cores = threads or host_threads()
     torch.set_num_threads(cores)
     wl = WORKLOADS[workload]
     cfg = get_config(wl['config'], device='cpu')
@@ -307,7 +313,7 @@ def run_reference(args):
     from refvsr_b200 import SRNet, get_config
     from refvsr_b200.modules import seeded_test_weights
     from refvsr_b200.synth import make_clip
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     wl = WORKLOADS[args.workload]
     cfg = get_config(wl['config'], device='cpu')
@@ -318,7 +324,7 @@ def run_reference(args):
     # bounded sample: full-size windows are minutes each on CPU, so a step is one steady-state window of the
     # same stream at 136x240 LR; the rate is scaled to 270x480 by the pixel ratio (optimistic for the CPU)
     h2, w2 = 136, 240
-    budget_s = float(os.environ.get('REFVSR_REF_BUDGET_S', '150'))
+    budget_s = float(os.environ.get('REFVSR_REF_BUDGET_S', '120'))
     n_frames = args.warmup + args.steps + 1
     lrs, refs = make_clip(min(n_frames, 24), h2, w2, wl['ref_scale'], seed=1234)
     nf = lrs.shape[0]

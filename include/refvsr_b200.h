@@ -91,6 +91,12 @@ typedef struct rv_conv_desc {
 
 int rv_conv2d(const rv_conv_desc* d, void* stream);
 
+/* space-to-depth by 2: out[(Y,X)][(ry*2+rx)*C + c] = src[(2Y+ry, 2X+rx)][c].  Turns the two stride-2
+ * convolutions of the path (ref_encoder2.0.0, RefVSR.py:45; aa2.align.p_conv.0, alignment.py:21) into
+ * stride-1 3x3 convolutions over 4C channels (weights re-indexed by packing.s2d_weights), so they run on
+ * the tcgen05 kernel.  H, W even; C*elemsize a multiple of 16. */
+int rv_space_to_depth2(const void* src, int H, int W, int C, int dtype, void* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Image / map preparation
  * ------------------------------------------------------------------------------------------------ */

@@ -67,6 +67,11 @@ class OracleOps:
         assert out.shape[:2] == o.shape[:2], (layer.name, out.shape, o.shape)
         out[..., :o.shape[2]] = o.to(out.dtype)
 
+    def space_to_depth2(self, src, out):
+        H, W, C = src.shape
+        z = src.view(H // 2, 2, W // 2, 2, C).permute(0, 2, 1, 3, 4).reshape(H // 2, W // 2, 4 * C)
+        out.copy_(z)
+
     # ---- image / pyramid prep ----
     def prep_image(self, src, out, mat12=None, pool2=False):
         x = src.detach().float().unsqueeze(0)

@@ -15,8 +15,10 @@
 //     they fit, otherwise streamed through the same ring as A.
 //   * D: fp32 accumulators in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of
 //     tile i+1.  Persistent CTAs walk the tile list round-robin.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2-5 = epilogue
-// (tcgen05.ld -> bias/act/gate/residual -> NHWC or pixel-shuffled store).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2-9 = two epilogue groups of
+// four warps; group g drains accumulator buffer g (tiles of parity g), so two tiles are in their epilogue
+// at any time while the MMA warp fills the next one (tcgen05.ld -> bias/act/gate/residual -> NHWC or
+// pixel-shuffled store).  The epilogue math is branch-free and fully unrolled (registers only).
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -32,7 +34,8 @@ struct TcP {
   uint32_t a_bytes, w_bytes;
   const uint8_t* wpack;
   const float* bias;
-  int act_pre, act_post;
+  float pre_slope, post_slope;   // act(v) = v > 0 ? v : v * slope  (none: 1, relu: 0, lrelu: 0.1 / 0.2)
+  int post_clamp3;               // clamp(-3, 3) after everything (AlignedConv2d affine map)
   const void* gate;
   int gate_cs;
   const void* res;
@@ -83,7 +86,7 @@ __device__ __forceinline__ void store16(T* p, const float v[16]) {
 }
 
 template <typename TI, typename TR, typename TO>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                const TcP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -194,14 +197,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     }
   } else {
     // ============================ epilogue ================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;  // accumulator buffer / tile parity owned by this group
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
     const int ty = m / TW, tx = m % TW;
     const TI* gate = reinterpret_cast<const TI*>(p.gate);
     const TR* res = reinterpret_cast<const TR*>(p.res);
     TO* out = reinterpret_cast<TO*>(p.out);
+    const float pre_slope = p.pre_slope, post_slope = p.post_slope;
     uint32_t t = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+      if ((int)(t & 1u) != grp) continue;
       const uint32_t acc = t & 1u, accph = (t >> 1) & 1u;
       const int oy = (tile / p.tiles_x) * TH + ty, ox = (tile % p.tiles_x) * TW + tx;
       const bool valid = (oy < p.Ho) && (ox < p.Wo);
@@ -210,37 +216,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride;
       for (int c0 = 0; c0 < p.NB; c0 += 16) {
+        const int n0 = nblk * p.NB + c0;
+        const bool live = valid && n0 < p.cout;
+        const bool full = (n0 + 16 <= p.cout);
+        const bool vec = full && p.vec_ok;
+        // issue the global loads of this chunk before waiting for TMEM
+        float g[16], rr[16];
+        if (live && gate) {
+          if (vec) {
+            load16<TI>(gate + pix * p.gate_cs + n0, g, true);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] = (n0 + j < p.cout) ? to_f(gate[pix * p.gate_cs + n0 + j]) : 0.f;
+          }
+        }
+        if (live && res) {
+          if (vec) {
+            load16<TR>(res + pix * p.res_cs + n0, rr, true);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rr[j] = (n0 + j < p.cout) ? to_f(res[pix * p.res_cs + n0 + j]) : 0.f;
+          }
+        }
         uint32_t r[16];
         tc::tmem_ld16(taddr + c0, r);
         tc::tmem_ld_wait();
-        const int n0 = nblk * p.NB + c0;
-        if (!valid || n0 >= p.cout) continue;
+        if (!live) continue;
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = apply_act(__uint_as_float(r[j]) + bias_s[c0 + j], p.act_pre);
-        const bool full = (n0 + 16 <= p.cout);
-        if (gate) {
-          if (full) {
-            float g[16];
-            load16<TI>(gate + pix * p.gate_cs + n0, g, p.vec_ok);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] *= g[j];
-          } else {
-            for (int j = 0; j < 16 && n0 + j < p.cout; ++j) v[j] *= to_f(gate[pix * p.gate_cs + n0 + j]);
-          }
+        for (int j = 0; j < 16; ++j) {
+          float x = __uint_as_float(r[j]) + bias_s[c0 + j];
+          x = x > 0.f ? x : x * pre_slope;
+          if (gate) x *= g[j];
+          if (res) x += rr[j];
+          x = x > 0.f ? x : x * post_slope;
+          v[j] = x;
         }
-        if (res) {
-          if (full) {
-            float g[16];
-            load16<TR>(res + pix * p.res_cs + n0, g, p.vec_ok);
+        if (p.post_clamp3) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += g[j];
-          } else {
-            for (int j = 0; j < 16 && n0 + j < p.cout; ++j) v[j] += to_f(res[pix * p.res_cs + n0 + j]);
-          }
+          for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], -3.f), 3.f);
         }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act_post);
         if (p.pixel_shuffle) {
           // n = 4c + 2a + b  ->  out[(2oy+a, 2ox+b)][c]; 16 n's = 4 consecutive c for each (a,b)
           const int cb = n0 >> 2;
@@ -248,14 +263,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           for (int ab = 0; ab < 4; ++ab) {
             const int a = ab >> 1, b = ab & 1;
             TO* o = out + ((size_t)(2 * oy + a) * (2 * p.Wo) + (2 * ox + b)) * p.out_cs + cb;
+            if (vec && sizeof(TO) == 2) {
+              TO pk[4];
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
-              if (n0 + 4 * cc + ab < p.cout) o[cc] = from_f<TO>(v[4 * cc + ab]);
+              for (int cc = 0; cc < 4; ++cc) pk[cc] = from_f<TO>(v[4 * cc + ab]);
+              *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(pk);
+            } else {
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc)
+                if (n0 + 4 * cc + ab < p.cout) o[cc] = from_f<TO>(v[4 * cc + ab]);
+            }
           }
-        } else if (full && p.vec_ok) {
+        } else if (vec) {
           store16<TO>(out + pix * p.out_cs + n0, v);
         } else {
-          for (int j = 0; j < 16 && n0 + j < p.cout; ++j) out[pix * p.out_cs + n0 + j] = from_f<TO>(v[j]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + j < p.cout) out[pix * p.out_cs + n0 + j] = from_f<TO>(v[j]);
         }
       }
       tc::tc_fence_before();
@@ -310,7 +334,7 @@ static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& 
     RV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  kern<<<grid, 192, smem, st>>>(tm0, tm1, p);
+  kern<<<grid, 320, smem, st>>>(tm0, tm1, p);
   RV_LAUNCH_CHECK("conv_tc");
   return RV_OK;
 }
@@ -358,7 +382,10 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   p.slots = std::min(p.slots, std::max(2, 2 * p.S));
   const size_t smem = 1024 + (size_t)p.slots * p.a_bytes + (p.resident ? w_all : (size_t)p.slots * p.w_bytes);
   p.wpack = (const uint8_t*)d->wpack; p.bias = d->bias;
-  p.act_pre = d->act_pre; p.act_post = d->act_post;
+  auto slope = [](int act) { return act == RV_ACT_RELU ? 0.f : act == RV_ACT_LRELU01 ? 0.1f : act == RV_ACT_LRELU02 ? 0.2f : 1.f; };
+  RV_REQUIRE(d->act_pre != RV_ACT_CLAMP3, "rv_conv2d(tc): clamp3 is only supported as act_post");
+  p.pre_slope = slope(d->act_pre); p.post_slope = slope(d->act_post);
+  p.post_clamp3 = d->act_post == RV_ACT_CLAMP3;
   p.gate = d->gate; p.gate_cs = d->gate_cs; p.res = d->res; p.res_cs = d->res_cs;
   p.out = d->out; p.out_cs = d->out_cs; p.pixel_shuffle = d->pixel_shuffle;
   p.fmt = d->in_dtype == RV_BF16 ? 1 : 0;

@@ -359,6 +359,21 @@ __global__ void gather_blocks_kernel(const uint8_t* __restrict__ value, int Hv, 
   else *reinterpret_cast<uint16_t*>(d) = *reinterpret_cast<const uint16_t*>(s);
 }
 
+// space-to-depth (factor 2): out[(Y,X)][(ry*2+rx)*C + c] = in[(2Y+ry, 2X+rx)][c]; 16-byte vectors
+__global__ void space_to_depth2_kernel(const uint4* __restrict__ src, int H, int W, int cv,
+                                       uint4* __restrict__ out) {
+  const int Ho = H / 2, Wo = W / 2;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Ho * Wo * 4 * cv) return;
+  int v = (int)(i % cv);
+  long long r = i / cv;
+  int sub = (int)(r % 4);
+  int p = (int)(r / 4);
+  int Y = p / Wo, X = p % Wo;
+  int ry = sub >> 1, rx = sub & 1;
+  out[((size_t)p * 4 + sub) * cv + v] = __ldg(src + ((size_t)(2 * Y + ry) * W + (2 * X + rx)) * cv + v);
+}
+
 template <typename T, int V>
 __global__ void aligned_sample_kernel(const T* __restrict__ x, int h, int w, int ks, int C,
                                       const float* __restrict__ affine, T* __restrict__ out) {
@@ -620,6 +635,18 @@ extern "C" int rv_aligned_sample(const void* x, int h, int w, int ks, int C, int
   RV_REQUIRE(x && affine && out && h > 0 && w > 0 && ks >= 1 && C > 0, "rv_aligned_sample: bad arguments");
   RV_REQUIRE(ks * h >= 2 && ks * w >= 2, "rv_aligned_sample: input too small for reflection padding");
   RV_DISPATCH_DTYPE(dtype, T, return (aligned_sample_launch<T>(x, h, w, ks, C, affine, out, (cudaStream_t)stream)));
+  return RV_OK;
+}
+
+extern "C" int rv_space_to_depth2(const void* src, int H, int W, int C, int dtype, void* out, void* stream) {
+  RV_REQUIRE(src && out && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "rv_space_to_depth2: H, W must be even (%d,%d)", H, W);
+  int rowbytes = C * dtype_size(dtype);
+  RV_REQUIRE(rowbytes % 16 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)out % 16 == 0),
+             "rv_space_to_depth2: pixel rows must be 16-byte multiples and aligned");
+  int cv = rowbytes / 16;
+  long long n = (long long)(H / 2) * (W / 2) * 4 * cv;
+  space_to_depth2_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, H, W, cv, (uint4*)out);
+  RV_LAUNCH_CHECK("space_to_depth2");
   return RV_OK;
 }
 

@@ -41,6 +41,7 @@ SIGNATURES = {
     'rv_version': (_I, []),
     'rv_launch_count': (C.c_uint64, []),
     'rv_conv2d': (_I, [C.POINTER(rv_conv_desc), _P]),
+    'rv_space_to_depth2': (_I, [_P, _I, _I, _I, _I, _P, _P]),
     'rv_prep_image': (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _P]),
     'rv_spynet_resize_norm': (_I, [_P, _I, _I, _P, _I, _I, _P]),
     'rv_avgpool2': (_I, [_P, _I, _I, _I, _P, _P]),
@@ -147,6 +148,12 @@ class CudaOps:
         d.nb = layer.nb
         d.k_real = layer.k_real
         _check(self.lib, self.lib.rv_conv2d(C.byref(d), self._stream()), f'rv_conv2d[{layer.name}]')
+
+    def space_to_depth2(self, src, out):
+        _chk_dev(src, out)
+        _check(self.lib, self.lib.rv_space_to_depth2(_ptr(src), src.shape[0], src.shape[1], src.shape[2],
+                                                     DTYPE_CODE[src.dtype], _ptr(out), self._stream()),
+               'rv_space_to_depth2')
 
     # -- image / pyramid prep ---------------------------------------------------------------------
     def prep_image(self, src, out, mat12=None, pool2=False):

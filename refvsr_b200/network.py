@@ -103,20 +103,20 @@ class Network(nn.Module):
     def _weights_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def _layer(self, name, srcs, stride=1, pad=None, bias_add=0.0):
+    def _layer(self, name, srcs, stride=1, pad=None, bias_add=0.0, s2d=False):
         """Packed weights of conv `name` (attribute path under self) for the given source layout."""
-        key = (name, tuple(srcs))
+        key = (name, tuple(srcs), s2d)
         hit = self._packed.get(key)
         if hit is not None:
             return hit
         mod = self.get_submodule(name)
-        k = mod.weight.shape[2]
-        dev = self._device
-        pc = self.ops.pack_conv(name, mod.weight, mod.bias, list(srcs), stride, k // 2 if pad is None else pad,
-                                self.act_dtype, dev, self.prefer_tc, bias_add) \
-            if hasattr(self.ops, 'pack_conv') else \
-            packing.pack_conv(name, mod.weight, mod.bias, list(srcs), stride, k // 2 if pad is None else pad,
-                              self.act_dtype, dev, self.prefer_tc, bias_add)
+        weight, srcs = mod.weight.detach(), list(srcs)
+        k = weight.shape[2]
+        pad = k // 2 if pad is None else pad
+        if s2d:
+            weight, srcs = packing.s2d_weights(weight, srcs, k // 2)
+        pack = self.ops.pack_conv if hasattr(self.ops, 'pack_conv') else packing.pack_conv
+        pc = pack(name, weight, mod.bias, srcs, stride, pad, self.act_dtype, self._device, self.prefer_tc, bias_add)
         self._packed[key] = pc
         return pc
 
@@ -130,6 +130,20 @@ class Network(nn.Module):
 
     def _conv(self, name, src0, src1, out, srcs, act_pre=ACT_NONE, act_post=ACT_NONE, gate=None, res=None,
               pixel_shuffle=False, stride=1, pad=None, bias_add=0.0):
+        k = self.get_submodule(name).weight.shape[2]
+        if (stride == 2 and self.prefer_tc and self.act_dtype != torch.float32 and k in (3, 5)
+                and (pad is None or pad == k // 2) and src0.shape[0] % 2 == 0 and src0.shape[1] % 2 == 0):
+            # stride-2 conv as a stride-1 3x3 conv over the space-to-depth input -> tensor-core kernel
+            z0 = self._buf(f's2d.{name}.0', (src0.shape[0] // 2, src0.shape[1] // 2, 4 * src0.shape[2]), src0.dtype)
+            self.ops.space_to_depth2(src0, z0)
+            z1 = None
+            if src1 is not None:
+                z1 = self._buf(f's2d.{name}.1', (src1.shape[0] // 2, src1.shape[1] // 2, 4 * src1.shape[2]), src1.dtype)
+                self.ops.space_to_depth2(src1, z1)
+            layer = self._layer(name, srcs, 1, 1, bias_add, s2d=True)
+            self.ops.conv2d(layer, z0, z1, out, gate=gate, res=res, act_pre=act_pre, act_post=act_post,
+                            pixel_shuffle=pixel_shuffle)
+            return out
         layer = self._layer(name, srcs, stride, pad, bias_add)
         self.ops.conv2d(layer, src0, src1, out, gate=gate, res=res, act_pre=act_pre, act_post=act_post,
                         pixel_shuffle=pixel_shuffle)
@@ -244,17 +258,17 @@ class Network(nn.Module):
     def _ref_features(self, ref):
         C, dt = self.mid_channels, self.act_dtype
         hr, wr = ref.shape[1], ref.shape[2]
-        ref8 = torch.empty((hr, wr, 8), dtype=dt, device=self._device)
+        ref8 = self._buf('re.ref8', (hr, wr, 8), dt)
         self.ops.prep_image(ref, ref8)
         e0 = self._conv('ref_encoder1.0.0', ref8, None, self._buf('re.e0', (hr, wr, C), dt), [(3, 8)], act_pre=ACT_LRELU02)
         e1 = self._conv('ref_encoder1.1.0', e0, None, self._buf('re.e1', (hr, wr, C), dt), [(C, C)], act_pre=ACT_LRELU02)
-        ref_feat = torch.empty((hr, wr, C), dtype=dt, device=self._device)
+        ref_feat = self._buf('re.feat', (hr, wr, C), dt)
         self._reslist('res1', 4, e1, ref_feat, 're.r1')
         h2, w2 = (hr - 1) // 2 + 1, (wr - 1) // 2 + 1
         d0 = self._conv('ref_encoder2.0.0', ref_feat, None, self._buf('re.d0', (h2, w2, C), dt), [(C, C)],
                         act_pre=ACT_LRELU02, stride=2)
         d1 = self._conv('ref_encoder2.1.0', d0, None, self._buf('re.d1', (h2, w2, C), dt), [(C, C)], act_pre=ACT_LRELU02)
-        ref_feat_down = torch.empty((h2, w2, C), dtype=dt, device=self._device)
+        ref_feat_down = self._buf('re.featd', (h2, w2, C), dt)
         self._reslist('res2', 4, d1, ref_feat_down, 're.r2')
         return ref8, ref_feat, ref_feat_down
 
@@ -291,17 +305,32 @@ class Network(nn.Module):
                         res=p0, act_post=ACT_LRELU02)
         affine = self._buf('aa2.aff', (ha, wa, 3), torch.float32)
         self._conv('aa2.align.p_conv.4', p1, None, affine, [(32, 32)], act_post=ACT_CLAMP3, pad=0, bias_add=1.0)
-        out = self._buf('aa2.out', (H2, W2, C), dt)
+        out = torch.empty((H2, W2, C), dtype=dt, device=self._device)
         self.ops.aligned_sample(warped, affine, ks, out)
         return out
 
-    # ---- RAP module (RefVSR.py:123-149) --------------------------------------------------------------
-    def _rap(self, lr, ref8, conf, conf_prop, idx, feat_prop, feat_prop_UP, ref_feat_down, ref_feat, tag):
+    def _frame_alignment(self, lr, ref):
+        """Everything the RAP module needs from one (LR, Ref) frame pair, all pure functions of the frame
+        (RefVSR.py:196-204,233-234 and the aa1 / aa2 calls of RefVSR.py:127,136): matching confidence, the
+        reference features gathered at LR resolution (aa1) and gathered + affinely re-sampled at 2x (aa2),
+        plus the NHWC copy of the LR frame.  Computed once per frame, reused by every window that contains it."""
         C, dt = self.mid_channels, self.act_dtype
+        h, w = lr.shape[1], lr.shape[2]
+        conf, idx = self._feature_match(lr, ref)
+        ref8, ref_feat, ref_feat_down = self._ref_features(ref)
+        aligned = torch.empty((h, w, C), dtype=dt, device=self._device)
+        self.ops.gather_blocks(ref_feat_down, idx, h, w, 1, aligned)     # aa1: scale 1, align=False -> pure gather
+        aligned_up = self._aa2(lr, ref8, idx, ref_feat, h, w)
+        lr8 = torch.empty((h, w, 8), dtype=dt, device=self._device)
+        self.ops.prep_image(lr, lr8)
+        return {'conf': conf, 'idx': idx, 'aligned': aligned, 'aligned_up': aligned_up, 'lr8': lr8}
+
+    # ---- RAP module (RefVSR.py:123-149) --------------------------------------------------------------
+    def _rap(self, fp, conf_prop, feat_prop, feat_prop_UP, tag):
+        C, dt = self.mid_channels, self.act_dtype
+        conf, aligned, aligned_up = fp['conf'], fp['aligned'], fp['aligned_up']
         h, w = conf.shape
-        # level 1: aa1 (scale 1, align=False) is a pure gather (attention.py:142-144)
-        aligned = self._buf('rap.al1', (h, w, C), dt)
-        self.ops.gather_blocks(ref_feat_down, idx, h, w, 1, aligned)
+        # level 1 (reference alignment already done per frame, see _frame_alignment)
         cp8 = self._buf('rap.cp8', (h, w, 8), dt)
         self.ops.conf_pair(conf_prop, conf, cp8, up2=False)
         a0 = self._conv('conf_fusion.0.0', cp8, None, self._buf('rap.a0', (h, w, 16), dt), [(2, 8)], act_pre=ACT_LRELU02)
@@ -314,7 +343,6 @@ class Network(nn.Module):
         self._reslist('feat_decoder', 8, fused, feat_out, 'rap.dec1')
 
         # level 2
-        aligned_up = self._aa2(lr, ref8, idx, ref_feat, h, w)
         up = self._conv('upsample1.upsample_conv', feat_out, None, self._buf('rap.up', (2 * h, 2 * w, C), dt), [(C, C)],
                         pixel_shuffle=True)
         fu = self._conv('feat_fusion2_1.0.0', feat_prop_UP, up, self._buf('rap.fu', (2 * h, 2 * w, C), dt),
@@ -368,7 +396,7 @@ class Network(nn.Module):
         pyr = st['pyr']
         for k in [k for k in pyr if k < a0]:
             del pyr[k]
-        for name in ('fw', 'bw', 'match', 'reff'):
+        for name in ('fw', 'bw', 'frame'):
             d = st[name]
             for k in [k for k in d if k < a0]:
                 del d[k]
@@ -390,10 +418,8 @@ class Network(nn.Module):
                 st['bw'][a0 + j] = (torch.zeros((h, w, 2), dtype=torch.float32, device=self._device) if zero_flow
                                     else self._spynet(pyramid(j), pyramid(j + 1), h, w))
         for j in range(need_match_from, t):
-            if a0 + j not in st['match']:
-                st['match'][a0 + j] = self._feature_match(lrs[j], refs[j])     # RefVSR.py:196-204
-            if a0 + j not in st['reff']:
-                st['reff'][a0 + j] = self._ref_features(refs[j])
+            if a0 + j not in st['frame']:
+                st['frame'][a0 + j] = self._frame_alignment(lrs[j], refs[j])
 
     # ------------------------------------------------------------------------------------------
     # forward (RefVSR.py:151-325)
@@ -448,7 +474,7 @@ class Network(nn.Module):
         # resets (reset_branch) keep sliding, so the caches stay valid across them.
         st = self._state.get(b)
         if st is None or caller_first or not self.reuse or is_train or st.get('shape') != (t, h, w, refs.shape[2], refs.shape[3]):
-            st = {'a0': 0, 'pyr': {}, 'fw': {}, 'bw': {}, 'match': {}, 'reff': {}, 'prev': st.get('prev') if st else None,
+            st = {'a0': 0, 'pyr': {}, 'fw': {}, 'bw': {}, 'frame': {}, 'prev': st.get('prev') if st else None,
                   'shape': (t, h, w, refs.shape[2], refs.shape[3])}
             self._state[b] = st
         else:
@@ -466,15 +492,6 @@ class Network(nn.Module):
         st['need_bw'] = list(range(mid, t - 1))
         st['need_fw'] = sorted(set(range(range_start, mid)) | ({mid} if mid < t - 1 else set()))
         self._frame_products(st, lrs, refs, a0, t, range_start)
-
-        lr8 = {}
-
-        def lr_nhwc(i):
-            if i not in lr8:
-                x = torch.empty((h, w, 8), dtype=dt, device=self._device)
-                ops.prep_image(lrs[i], x)
-                lr8[i] = x
-            return lr8[i]
 
         vis = {'vis': collections.OrderedDict()} if is_log else None
 
@@ -494,12 +511,10 @@ class Network(nn.Module):
                 feat_prop, conf_prop, feat_prop_UP = wf, wc, wu
                 if is_log and i == mid:
                     vis['vis']['BW_LR_next_warp'] = self._warp_image(lrs[i + 1], flow)
-            agg = self._prop_resblocks('backward_resblocks', lr_nhwc(i), feat_prop,
+            fp = st['frame'][a0 + i]
+            agg = self._prop_resblocks('backward_resblocks', fp['lr8'], feat_prop,
                                        self._buf('bw.agg', (h, w, C), dt), 'bw.rb')
-            conf, idx = st['match'][a0 + i]
-            ref8, ref_feat, ref_feat_down = st['reff'][a0 + i]
-            feat_prop, feat_prop_UP, conf_prop = self._rap(lrs[i], ref8, conf, conf_prop, idx, agg, feat_prop_UP,
-                                                           ref_feat_down, ref_feat, f'bw.rap{i % 2}')
+            feat_prop, feat_prop_UP, conf_prop = self._rap(fp, conf_prop, agg, feat_prop_UP, f'bw.rap{i % 2}')
         backward_feat_UP, conf_bw = feat_prop_UP, conf_prop
         # (the forward branch writes 'fw.*' buffers only, so these stay intact)
 
@@ -534,12 +549,10 @@ class Network(nn.Module):
                 feat_prop, feat_prop_UP, conf_prop = wf, wu, wc
             if is_log and i == mid and flow is not None:
                 vis['vis']['FW_LR_prev_warp'] = self._warp_image(lrs[i - 1], flow)
-            agg = self._prop_resblocks('forward_resblocks', lr_nhwc(i), feat_prop,
+            fp = st['frame'][a0 + i]
+            agg = self._prop_resblocks('forward_resblocks', fp['lr8'], feat_prop,
                                        self._buf('fw.agg', (h, w, C), dt), 'fw.rb')
-            conf, idx = st['match'][a0 + i]
-            ref8, ref_feat, ref_feat_down = st['reff'][a0 + i]
-            feat_prop, feat_prop_UP, conf_prop = self._rap(lrs[i], ref8, conf, conf_prop, idx, agg, feat_prop_UP,
-                                                           ref_feat_down, ref_feat, f'fw.rap{i % 2}')
+            feat_prop, feat_prop_UP, conf_prop = self._rap(fp, conf_prop, agg, feat_prop_UP, f'fw.rap{i % 2}')
             if (is_train and i == 0) or (not is_train and i == mid):           # RefVSR.py:279-283
                 st['prev'] = {'feat': feat_prop.clone(), 'featUP': feat_prop_UP.clone(), 'conf': conf_prop.clone(),
                               'flow': st['fw'][a0 + i].clone() if (a0 + i) in st['fw'] else None}
@@ -549,7 +562,7 @@ class Network(nn.Module):
 
         if is_log and _cget(self.config, 'save_sample', False):
             ev = collections.OrderedDict()
-            ev['conf_map'] = st['match'][a0 + mid][0].view(1, 1, h, w).clone()
+            ev['conf_map'] = st['frame'][a0 + mid]['conf'].view(1, 1, h, w).clone()
             ev['conf_map_prop_backward'] = conf_bw.view(1, 1, h, w).clone()
             ev['conf_map_prop_forward'] = conf_prop.view(1, 1, h, w).clone()
             ev['conf_map_prop'] = torch.maximum(ev['conf_map_prop_backward'], ev['conf_map_prop_forward'])

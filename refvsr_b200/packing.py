@@ -46,6 +46,29 @@ def _expand_inputs(weight, srcs):
     return torch.cat(parts, 1)
 
 
+def s2d_weights(weight, srcs, pad):
+    """Re-index a stride-2 k x k convolution (k in {3,5}, pad = k//2) as a stride-1 3x3 convolution over the
+    space-to-depth input:  iy = 2*oy + ky - pad = 2*(oy + dy) + ry  with dy = floor((ky-pad)/2), ry = (ky-pad) mod 2,
+    so  W'[n, (ry*2+rx)*alloc + c, dy+1, dx+1] = W[n, c, ky, kx].  Returns (W', srcs') with every s2d channel
+    marked real (padding channels simply carry zero weights)."""
+    cout, cin, kh, kw = weight.shape
+    assert kh == kw and kh in (3, 5) and pad == kh // 2
+    outs, new_srcs, o = [], [], 0
+    for real, alloc in srcs:
+        w = weight[:, o:o + real].float()
+        o += real
+        wp = weight.new_zeros((cout, 4 * alloc, 3, 3), dtype=torch.float32)
+        for ky in range(kh):
+            dy, ry = (ky - pad) // 2, (ky - pad) % 2
+            for kx in range(kw):
+                dx, rx = (kx - pad) // 2, (kx - pad) % 2
+                base = (ry * 2 + rx) * alloc
+                wp[:, base:base + real, dy + 1, dx + 1] = w[:, :, ky, kx]
+        outs.append(wp)
+        new_srcs.append((4 * alloc, 4 * alloc))
+    return torch.cat(outs, 1), new_srcs
+
+
 def pack_simt(weight, srcs):
     w = _expand_inputs(weight.float(), srcs)            # (cout, ct, kh, kw)
     cout, ct, kh, kw = w.shape

@@ -26,7 +26,7 @@ def test_schedule_matches_reference_golden(name, oracle_ops):
         assert psnr(o[0], g) > 95.0 and (o[0] - g).abs().max() < 2e-3
         if k == 0:
             st = net.Network._state[0]
-            mism = np.mean([(st['match'][i][1].numpy() != golden['idx_0'][i]).mean() for i in range(spec['T'])])
+            mism = np.mean([(st['frame'][i]['idx'].numpy() != golden['idx_0'][i]).mean() for i in range(spec['T'])])
             assert mism <= 1e-3
 
 
@@ -39,7 +39,7 @@ def test_reuse_on_off_and_unused_flows(oracle_ops):
         res[reuse] = [net(wl, wr, first)['result'] for k, wl, wr, first in sliding_windows(lrs, refs, spec['T'])]
         st = net.Network._state[0]
         if reuse:   # steady state keeps only what the next window can still use
-            assert len(st['match']) <= spec['T'] and len(st['fw']) <= spec['T'] and len(st['bw']) <= spec['T']
+            assert len(st['frame']) <= spec['T'] and len(st['fw']) <= spec['T'] and len(st['bw']) <= spec['T']
     for a, b in zip(res[True], res[False]):
         assert torch.equal(a, b)
 

@@ -195,6 +195,36 @@ def test_spynet_glue(cuda_ops, oracle_ops):
     close(got, exp, 1e-5, 'flow_resize')
 
 
+def test_space_to_depth(cuda_ops, oracle_ops):
+    x = rnd((14, 22, 48), 1, torch.float16)
+    got, exp = both(oracle_ops.space_to_depth2, cuda_ops.space_to_depth2, (x,), (7, 11, 192), torch.float16)
+    assert torch.equal(got.cpu(), exp)
+
+
+def test_stride2_conv_via_space_to_depth_on_tensor_cores(cuda_ops, oracle_ops):
+    """ref_encoder2.0.0 (3x3 s2) and aa2.align.p_conv.0 (5x5 s2, two sources) through s2d + tcgen05"""
+    for k, srcs in ((3, [(48, 48)]), (5, [(32, 32), (32, 32)])):
+        cin = sum(r for r, _ in srcs)
+        w = rnd((32, cin, k, k), 1, scale=1.5 / (cin * k * k) ** 0.5).half().float()
+        b = rnd((32,), 2, scale=0.1)
+        xs = [rnd((30, 44, a), 10 + i, torch.float16) for i, (_, a) in enumerate(srcs)]
+        lo = oracle_ops.pack_conv('ref', w, b, srcs, 2, k // 2, torch.float16, 'cpu', False)
+        exp = torch.zeros((15, 22, 32))
+        oracle_ops.conv2d(lo, xs[0], xs[1] if len(xs) > 1 else None, exp, act_pre=ACT_LRELU02)
+        w2, srcs2 = packing.s2d_weights(w, srcs, k // 2)
+        lc = packing.pack_conv('s2d', w2, b, srcs2, 1, 1, torch.float16, 'cuda', True)
+        assert lc.impl == IMPL_TC
+        zs = []
+        for x in xs:
+            z = torch.empty((15, 22, 4 * x.shape[2]), dtype=torch.float16, device='cuda')
+            cuda_ops.space_to_depth2(x.cuda(), z)
+            zs.append(z)
+        out = torch.zeros((15, 22, 32), dtype=torch.float16, device='cuda')
+        cuda_ops.conv2d(lc, zs[0], zs[1] if len(zs) > 1 else None, out, act_pre=ACT_LRELU02)
+        torch.cuda.synchronize()
+        close(out, exp, 4e-3, f's2d conv k={k}')
+
+
 @pytest.mark.parametrize('ks', [1, 2])
 def test_gather_blocks(cuda_ops, oracle_ops, ks):
     hq, wq, C = 14, 22, 48

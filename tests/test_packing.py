@@ -66,3 +66,24 @@ def test_pack_conv_chooses_impl():
     assert packing.pack_conv('a', w, b, [(48, 48)], 1, 1, torch.float16, 'cpu', False).impl == IMPL_SIMT
     p = packing.pack_conv('a', w, b, [(48, 48)], 1, 1, torch.float16, 'cpu', True, bias_add=1.0)
     assert torch.equal(p.bias, torch.ones(48))
+
+
+@pytest.mark.parametrize('k,srcs', [(3, [(48, 48)]), (5, [(32, 32), (32, 32)]), (5, [(3, 8)])])
+def test_space_to_depth_reindexing_equals_stride2_conv(k, srcs, oracle_ops):
+    """stride-2 conv == stride-1 3x3 conv over the space-to-depth input with packing.s2d_weights"""
+    import torch.nn.functional as F
+    cin = sum(r for r, _ in srcs)
+    w, b = torch.randn(7, cin, k, k), torch.randn(7)
+    xs = [torch.randn(12, 18, a) for _, a in srcs]
+    xin = torch.cat([x[..., :r].permute(2, 0, 1) for x, (r, _) in zip(xs, srcs)], 0).unsqueeze(0)
+    exp = F.conv2d(xin, w, b, stride=2, padding=k // 2)[0].permute(1, 2, 0)
+    w2, srcs2 = packing.s2d_weights(w, srcs, k // 2)
+    zs = []
+    for x in xs:
+        z = torch.empty(6, 9, 4 * x.shape[2])
+        oracle_ops.space_to_depth2(x, z)
+        zs.append(z)
+    layer = oracle_ops.pack_conv('s2d', w2, b, srcs2, 1, 1, torch.float32, 'cpu', False)
+    out = torch.zeros(6, 9, 7)
+    oracle_ops.conv2d(layer, zs[0], zs[1] if len(zs) > 1 else None, out)
+    assert (out - exp).abs().max() < 1e-4
