@@ -116,13 +116,20 @@ def kernel_rooflines(net, peaks):
     nrot = max(2, int(160e6 // (H * W * C * e)) + 1)          # rotate through ~160 MB > 126 MB L2
 
     def timeit(fn, iters=30, warm=5):
+        # the `iters` launches are captured into one CUDA graph so the number is device time per launch, not the
+        # Python / ctypes / tensor-map-encode launch rate (which is what a plain loop measures for ~25 us kernels)
         for i in range(warm):
             fn(i)
         torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(iters):
+                fn(i)
+        graph.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(iters):
-            fn(i)
+        graph.replay()
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters * 1e-3

@@ -85,6 +85,24 @@ __device__ __forceinline__ void store16(T* p, const float v[16]) {
   }
 }
 
+// all MMAs of one pipeline stage: KH vertical taps x ksteps (<= 4) K-slices of 16 channels.  Descriptor
+// start addresses advance by +2 (32 bytes) per K-slice and by one tile row block per tap.
+template <int KH>
+__device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t idesc, int ksteps,
+                                           uint32_t b_tap, uint32_t& accumulate) {
+#pragma unroll
+  for (int ky = 0; ky < KH; ++ky) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < ksteps) {
+        tc::umma_f16(d_tmem, ad + (uint64_t)(ky * (TW * 128 / 16) + k * 2), bd + (uint64_t)(ky * b_tap + k * 2), idesc,
+                     accumulate);
+        accumulate = 1;
+      }
+    }
+  }
+}
+
 template <typename TI, typename TR, typename TO>
 __global__ void __launch_bounds__(320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
@@ -137,60 +155,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         for (int s = 0; s < p.S; ++s)
           tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_w, smemW + (size_t)s * p.w_bytes, p.w_bytes);
       }
-      uint32_t it = 0;
+      const uint32_t tx_bytes = p.a_bytes + (p.resident ? 0u : p.w_bytes);
+      int slot = 0;
+      uint32_t ph = 0;
+      int ty0 = blockIdx.x / p.tiles_x, tx0 = blockIdx.x - ty0 * p.tiles_x;   // tile coordinates, advanced incrementally
+      const int dty = gridDim.x / p.tiles_x, dtx = gridDim.x - dty * p.tiles_x;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int y0 = (tile / p.tiles_x) * TH, x0 = (tile % p.tiles_x) * TW;
-        for (int s = 0; s < p.S; ++s, ++it) {
-          const int slot = it % p.slots;
-          const uint32_t ph = (it / p.slots) & 1u;
+        const int yc = ty0 * TH - p.pad, xc = tx0 * TW - p.pad;
+        int kx = 0, ch = 0;
+        for (int s = 0; s < p.S; ++s) {
           tc::mbar_wait(&bar_empty[slot], ph ^ 1u);
-          const int kx = s / nchunks, ch = s - kx * nchunks;
-          tc::mbar_expect_tx(&bar_full[slot], p.a_bytes + (p.resident ? 0u : p.w_bytes));
+          tc::mbar_expect_tx(&bar_full[slot], tx_bytes);
+          uint8_t* dstA = smemA + (size_t)slot * p.a_bytes;
           if (ch < p.nch0)
-            tc::tma_load_3d(&tm0, &bar_full[slot], smemA + (size_t)slot * p.a_bytes, ch * 64,
-                            x0 + kx - p.pad, y0 - p.pad);
+            tc::tma_load_3d(&tm0, &bar_full[slot], dstA, ch * 64, xc + kx, yc);
           else
-            tc::tma_load_3d(&tm1, &bar_full[slot], smemA + (size_t)slot * p.a_bytes,
-                            (ch - p.nch0) * 64, x0 + kx - p.pad, y0 - p.pad);
+            tc::tma_load_3d(&tm1, &bar_full[slot], dstA, (ch - p.nch0) * 64, xc + kx, yc);
           if (!p.resident)
-            tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_full[slot],
-                          smemW + (size_t)slot * p.w_bytes, p.w_bytes);
+            tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_full[slot], smemW + (size_t)slot * p.w_bytes, p.w_bytes);
+          if (++ch == nchunks) { ch = 0; ++kx; }
+          if (++slot == p.slots) { slot = 0; ph ^= 1u; }
         }
+        tx0 += dtx; ty0 += dty;
+        if (tx0 >= p.tiles_x) { tx0 -= p.tiles_x; ++ty0; }
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
+    // One thread issues every tcgen05.mma of the CTA, so its instruction stream is kept minimal:
+    // descriptors are 64-bit bases plus small immediates, the tap loop is unrolled per kernel height.
     if (lane == 0) {
       const uint32_t idesc = tc::umma_idesc(p.fmt, 128, p.NB);
-      if (p.resident) {
-        tc::mbar_wait(&bar_w, 0);
-      }
-      uint32_t it = 0, t = 0;
+      const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(smemA));
+      const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(smemW));
+      const uint32_t a_step = p.a_bytes >> 4, w_step = p.w_bytes >> 4, b_tap = (uint32_t)(p.NB * 128) >> 4;
+      if (p.resident) tc::mbar_wait(&bar_w, 0);
+      int slot = 0;
+      uint32_t ph = 0, t = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
         const uint32_t acc = t & 1u, accph = (t >> 1) & 1u;
         tc::mbar_wait(&bar_tempty[acc], accph ^ 1u);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
         uint32_t accumulate = 0;
-        for (int s = 0; s < p.S; ++s, ++it) {
-          const int slot = it % p.slots;
-          const uint32_t ph = (it / p.slots) & 1u;
-          tc::mbar_wait(&bar_full[slot], ph);
-          tc::tc_fence_after();
-          const int kx = s / nchunks, ch = s - kx * nchunks;
+        int ch = 0;
+        for (int s = 0; s < p.S; ++s) {
           const int crem = (ch < p.nch0) ? (p.c0 - ch * 64) : (p.c1 - (ch - p.nch0) * 64);
           const int ksteps = (min(crem, 64) + 15) >> 4;
-          const uint32_t a0 = tc::smem_u32(smemA + (size_t)slot * p.a_bytes);
-          const uint32_t b0 = tc::smem_u32(smemW + (size_t)(p.resident ? s : slot) * p.w_bytes);
-          for (int ky = 0; ky < p.kh; ++ky) {
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t ad = tc::umma_desc_sw128(a0 + ky * (TW * 128) + k * 32);
-              const uint64_t bd = tc::umma_desc_sw128(b0 + ky * (p.NB * 128) + k * 32);
-              tc::umma_f16(d_tmem, ad, bd, idesc, accumulate);
-              accumulate = 1;
-            }
+          const uint64_t ad = adesc0 + (uint64_t)((uint32_t)slot * a_step);
+          const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)(p.resident ? s : slot) * w_step);
+          tc::mbar_wait(&bar_full[slot], ph);
+          tc::tc_fence_after();
+          switch (p.kh) {
+            case 1: issue_taps<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
+            case 3: issue_taps<3>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
+            case 5: issue_taps<5>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
+            case 7: issue_taps<7>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
+            default:
+              for (int ky = 0; ky < p.kh; ++ky)
+                for (int k = 0; k < ksteps; ++k) {
+                  tc::umma_f16(d_tmem, ad + (uint64_t)(ky * (TW * 128 / 16) + k * 2), bd + (uint64_t)(ky * b_tap + k * 2), idesc, accumulate);
+                  accumulate = 1;
+                }
           }
           tc::umma_commit(&bar_empty[slot]);  // frees the smem slot when these MMAs retire
+          if (++ch == nchunks) ch = 0;
+          if (++slot == p.slots) { slot = 0; ph ^= 1u; }
         }
         tc::umma_commit(&bar_tfull[acc]);
       }
@@ -206,24 +236,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     TO* out = reinterpret_cast<TO*>(p.out);
     const float pre_slope = p.pre_slope, post_slope = p.post_slope;
     uint32_t t = 0;
+    constexpr int PRE = 4;  // chunks whose residual / gate vectors are prefetched before the accumulator wait
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
       if ((int)(t & 1u) != grp) continue;
       const uint32_t acc = t & 1u, accph = (t >> 1) & 1u;
       const int oy = (tile / p.tiles_x) * TH + ty, ox = (tile % p.tiles_x) * TW + tx;
       const bool valid = (oy < p.Ho) && (ox < p.Wo);
       const size_t pix = (size_t)oy * p.Wo + ox;
+      // ---- prefetch: one DRAM round trip per tile, overlapped with the MMAs of this tile ----
+      uint4 rp[PRE][2], gp[PRE][2];
+      bool pre_ok[PRE];
+#pragma unroll
+      for (int c = 0; c < PRE; ++c) {
+        const int n0 = nblk * p.NB + c * 16;
+        pre_ok[c] = valid && (c * 16 < p.NB) && (n0 + 16 <= p.cout) && p.vec_ok;
+        if (pre_ok[c] && res != nullptr && sizeof(TR) == 2) {
+          const uint4* q4 = reinterpret_cast<const uint4*>(res + pix * p.res_cs + n0);
+          rp[c][0] = __ldg(q4);
+          rp[c][1] = __ldg(q4 + 1);
+        }
+        if (pre_ok[c] && gate != nullptr) {
+          const uint4* q4 = reinterpret_cast<const uint4*>(gate + pix * p.gate_cs + n0);
+          gp[c][0] = __ldg(q4);
+          gp[c][1] = __ldg(q4 + 1);
+        }
+      }
       tc::mbar_wait(&bar_tfull[acc], accph);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride;
-      for (int c0 = 0; c0 < p.NB; c0 += 16) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const int c0 = c * 16;
+        if (c0 >= p.NB) break;
         const int n0 = nblk * p.NB + c0;
         const bool live = valid && n0 < p.cout;
         const bool full = (n0 + 16 <= p.cout);
         const bool vec = full && p.vec_ok;
-        // issue the global loads of this chunk before waiting for TMEM
+        const bool pre = (c < PRE) && pre_ok[c < PRE ? c : 0];
         float g[16], rr[16];
         if (live && gate) {
-          if (vec) {
+          if (pre) {
+            const TI* tg = reinterpret_cast<const TI*>(&gp[c < PRE ? c : 0][0]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] = to_f(tg[j]);
+          } else if (vec) {
             load16<TI>(gate + pix * p.gate_cs + n0, g, true);
           } else {
 #pragma unroll
@@ -231,7 +287,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           }
         }
         if (live && res) {
-          if (vec) {
+          if (pre && sizeof(TR) == 2) {
+            const TR* tr = reinterpret_cast<const TR*>(&rp[c < PRE ? c : 0][0]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rr[j] = to_f(tr[j]);
+          } else if (vec) {
             load16<TR>(res + pix * p.res_cs + n0, rr, true);
           } else {
 #pragma unroll
@@ -345,7 +405,7 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   RV_REQUIRE(d->c0 % 8 == 0 && (!d->src1 || d->c1 % 8 == 0), "rv_conv2d(tc): channel counts must be multiples of 8");
   RV_REQUIRE(((uintptr_t)d->src0 % 16 == 0) && ((uintptr_t)d->src1 % 16 == 0) && ((uintptr_t)d->wpack % 16 == 0),
              "rv_conv2d(tc): src/wpack must be 16-byte aligned");
-  RV_REQUIRE(d->nb >= 16 && d->nb <= 256 && d->nb % 16 == 0, "rv_conv2d(tc): nb=%d must be a multiple of 16 in [16,256]", d->nb);
+  RV_REQUIRE(d->nb >= 16 && d->nb <= 96 && d->nb % 16 == 0, "rv_conv2d(tc): nb=%d must be a multiple of 16 in [16,96]", d->nb);
   RV_REQUIRE(d->kh >= 1 && d->kh <= 7 && d->kw >= 1 && d->kw <= 7, "rv_conv2d(tc): kernel size up to 7x7");
   RV_REQUIRE(!d->pixel_shuffle || d->cout % 4 == 0, "rv_conv2d: pixel_shuffle needs cout %% 4 == 0");
   if (g_num_sms == 0) {

@@ -8,10 +8,13 @@ confined to *how* results are obtained, never to what they are:
 
   * activations are NHWC f16/bf16/f32 buffers; concat / bias / activation / gating / residual /
     pixel-shuffle are fused into the conv kernels;
-  * exact reuse across sliding windows: optical flows, (conf, index) maps and reference
-    features are pure functions of frame content; a window that slides by one frame (the reference's own
-    assumption when it reuses forward_*_prev, RefVSR.py:256-260) re-computes only what the new frame
-    brings.  Flows the reference computes but never consumes are skipped;
+  * exact reuse across sliding windows: optical flows, matching confidence / index maps and
+    the aligned reference features (aa1 / aa2 outputs) are pure functions of frame content; a window that
+    slides by one frame (the reference's own assumption when it reuses forward_*_prev, RefVSR.py:256-260)
+    re-computes only what the new frame brings.  Flows the reference computes but never consumes are skipped;
+  * every buffer of a step lives at a fixed address (pooled scratch + a ring of T per-frame slots), so a
+    whole window is ONE CUDA-graph launch after its first occurrence (~750 kernels, no host work between
+    them); graphs are keyed by (ring phase, window kind, work list);
   * no gc.collect()/empty_cache() (RefVSR.py:206-208), no host synchronisation inside forward.
 """
 import collections
@@ -32,10 +35,6 @@ def _cget(config, name, default):
     except (AttributeError, KeyError):
         return default
     return default if v is None else v
-
-
-def _pad8(c):
-    return (c + 7) // 8 * 8
 
 
 class Network(nn.Module):
@@ -59,7 +58,8 @@ class Network(nn.Module):
         self.max_frame_itr_num = config.reset_branch
         self._state = {}
         self._packed = {}
-        self._packed_key = None
+        self._graphs = {}
+        self._mat12 = None
         self._ops = ops
         prec = _cget(config, 'b200_precision', None)
         if prec is None:
@@ -71,13 +71,20 @@ class Network(nn.Module):
         self.match_mode = _cget(config, 'b200_match', 'single' if prec == 'fp16' else 'split')
         self.prefer_tc = bool(_cget(config, 'b200_tensor_cores', True))
         self.reuse = bool(_cget(config, 'b200_reuse', True))
+        self.use_graphs = bool(_cget(config, 'b200_cuda_graphs', True))
         self._bufs = {}
         self._device = torch.device('cpu')
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module._packed.clear())
+        self._b = 0
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    def _invalidate(self):
+        self._packed.clear()
+        self._graphs.clear()
+        self._mat12 = None
 
     def _apply(self, fn, *a, **k):
-        # .to()/.cuda()/.half() move or convert parameters: packed kernels weights must be rebuilt
-        self._packed.clear()
+        # .to()/.cuda()/.half() move or convert parameters: packed weights, graphs and buffers must be rebuilt
+        self._invalidate()
         self._bufs.clear()
         self._state.clear()
         return super()._apply(fn, *a, **k)
@@ -94,14 +101,11 @@ class Network(nn.Module):
 
     def set_ops(self, ops):
         self._ops = ops
-        self._packed.clear()
+        self._invalidate()
 
     def reset_state(self):
         self._state.clear()
         self.frame_itr_num = 0
-
-    def _weights_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _layer(self, name, srcs, stride=1, pad=None, bias_add=0.0, s2d=False):
         """Packed weights of conv `name` (attribute path under self) for the given source layout."""
@@ -184,51 +188,55 @@ class Network(nn.Module):
         return out
 
     # ---- SPyNet (SPyNet.py:49-139) ----------------------------------------------------------------
-    def _pyramid(self, img):
-        """img (3,h,w) fp32 -> list of 6 normalised levels, coarsest first, each (H,W,3) fp32."""
-        h, w = img.shape[1], img.shape[2]
+    @staticmethod
+    def _pyr_shapes(h, w):
         w_up = w if w % 32 == 0 else 32 * (w // 32 + 1)
         h_up = h if h % 32 == 0 else 32 * (h // 32 + 1)
-        lv = [torch.empty((h_up, w_up, 3), dtype=torch.float32, device=self._device)]
-        self.ops.spynet_resize_norm(img, lv[0])
-        for _ in range(5):
-            p = lv[-1]
-            q = torch.empty((p.shape[0] // 2, p.shape[1] // 2, 3), dtype=torch.float32, device=self._device)
-            self.ops.avgpool2(p, q)
-            lv.append(q)
-        return lv[::-1]
+        return [(h_up >> (5 - l), w_up >> (5 - l)) for l in range(6)]      # coarsest first
 
-    def _spynet(self, pyr_ref, pyr_supp, h, w):
-        """flow from ref to supp, (h,w,2) fp32.  pyr_*: outputs of _pyramid."""
+    def _pyramid(self, img, slot):
+        """img (3,h,w) fp32 -> 6 normalised levels, coarsest first, each (H,W,3) fp32, in ring slot `slot`."""
+        shapes = self._pyr_shapes(img.shape[1], img.shape[2])
+        lv = [self._buf(f'ring{self._b}.pyr{l}.{slot}', (H, W, 3), torch.float32) for l, (H, W) in enumerate(shapes)]
+        self.ops.spynet_resize_norm(img, lv[5])
+        for l in range(4, -1, -1):
+            self.ops.avgpool2(lv[l + 1], lv[l])
+        return lv
+
+    def _spynet(self, pyr_ref, pyr_supp, out):
+        """flow from ref to supp into `out` (h,w,2) fp32.  pyr_*: outputs of _pyramid."""
         dt = self.act_dtype
         flow = None
         for level in range(6):
             r, s = pyr_ref[level], pyr_supp[level]
             H, W = r.shape[0], r.shape[1]
             x8 = self._buf('spy.x8', (H, W, 8), dt)
-            flow_up = torch.empty((H, W, 2), dtype=torch.float32, device=self._device)
+            flow_up = self._buf('spy.fu', (H, W, 2), torch.float32)
             self.ops.spynet_level_input(r, s, flow, x8, flow_up)
             pre = f'FlowNet.basic_module.{level}.basic_module'
             a = self._conv(f'{pre}.0.conv', x8, None, self._buf('spy.a', (H, W, 32), dt), [(8, 8)], act_pre=ACT_RELU)
             b = self._conv(f'{pre}.1.conv', a, None, self._buf('spy.b', (H, W, 64), dt), [(32, 32)], act_pre=ACT_RELU)
             c = self._conv(f'{pre}.2.conv', b, None, self._buf('spy.c', (H, W, 32), dt), [(64, 64)], act_pre=ACT_RELU)
             d = self._conv(f'{pre}.3.conv', c, None, self._buf('spy.d', (H, W, 16), dt), [(32, 32)], act_pre=ACT_RELU)
-            flow = torch.empty((H, W, 2), dtype=torch.float32, device=self._device)
+            flow = self._buf('spy.fl', (H, W, 2), torch.float32)
             self._conv(f'{pre}.4.conv', d, None, flow, [(16, 16)], res=flow_up)   # flow_up + residue (SPyNet.py:95)
-        out = torch.empty((h, w, 2), dtype=torch.float32, device=self._device)
         self.ops.flow_resize(flow, out)     # SPyNet.py:129-137; RefVSR.py:184,189 resize is the identity
         return out
 
     # ---- feature matching (attention.py:58-100) -----------------------------------------------------
+    def _sub_mean_mat(self):
+        if self._mat12 is None:
+            sm = self.feature_match.sub_mean
+            wm = sm.weight.detach().float().reshape(3, 3).cpu()
+            bm = sm.bias.detach().float().cpu()
+            self._mat12 = [float(v) for r in range(3) for v in (wm[r, 0], wm[r, 1], wm[r, 2], bm[r])]
+        return self._mat12
+
     def _match_features(self, img, pool2, tag):
-        sm = self.feature_match.sub_mean
-        wm = sm.weight.detach().float().reshape(3, 3).cpu()
-        bm = sm.bias.detach().float().cpu()
-        mat12 = [float(v) for r in range(3) for v in (wm[r, 0], wm[r, 1], wm[r, 2], bm[r])]
         H, W = (img.shape[1] // 2, img.shape[2] // 2) if pool2 else (img.shape[1], img.shape[2])
         dt = self.act_dtype
         x8 = self._buf(tag + '.x8', (H, W, 8), dt)
-        self.ops.prep_image(img, x8, mat12=mat12, pool2=pool2)
+        self.ops.prep_image(img, x8, mat12=self._sub_mean_mat(), pool2=pool2)
         f1 = self._conv('feature_match.feature_extract.0', x8, None, self._buf(tag + '.f1', (H, W, 64), dt),
                         [(3, 8)], act_pre=ACT_RELU)
         f2 = self._conv('feature_match.feature_extract.2', f1, None, self._buf(tag + '.f2', (H, W, 64), dt),
@@ -237,8 +245,8 @@ class Network(nn.Module):
                         [(64, 64)], act_pre=ACT_LRELU02)
         return f3
 
-    def _feature_match(self, lr, ref):
-        """-> conf (h,w) fp32, idx (h*w,) int32 indexing the (hr/2 x wr/2) reference feature grid."""
+    def _feature_match(self, lr, ref, conf, idx):
+        """conf (h,w) fp32, idx (h*w,) int32 indexing the (hr/2 x wr/2) reference feature grid."""
         h, w = lr.shape[1], lr.shape[2]
         split = self.match_mode == 'split'
         kpad = 448 if split else 192
@@ -249,10 +257,7 @@ class Network(nn.Module):
         R = ref_f.shape[0] * ref_f.shape[1]
         B = self._buf('fm.B', (R, kpad), torch.float16)
         self.ops.patch_pack(ref_f, B, 2 if split else 0)
-        conf = torch.empty((h, w), dtype=torch.float32, device=self._device)
-        idx = torch.empty((h * w,), dtype=torch.int32, device=self._device)
         self.ops.match_argmax(A, B, conf, idx, impl=1 if self.prefer_tc else 0)
-        return conf, idx
 
     # ---- reference encoders (RefVSR.py:233-234,274-275) ----------------------------------------------
     def _ref_features(self, ref):
@@ -283,8 +288,8 @@ class Network(nn.Module):
         self._conv('aa2.align.conv1.2.conv2', t, None, out, [(32, 32)], res=a, act_post=ACT_LRELU02)
         return out
 
-    def _aa2(self, lr, ref8, idx, ref_feat, h, w):
-        """AlignedAttention scale=2 + AlignedConv2d (attention.py:131-159): -> (2h,2w,C)."""
+    def _aa2(self, lr, ref8, idx, ref_feat, h, w, out):
+        """AlignedAttention scale=2 + AlignedConv2d (attention.py:131-159) -> out (2h,2w,C)."""
         C, dt = self.mid_channels, self.act_dtype
         ks = self.aa2.scale
         H2, W2 = 2 * h, 2 * w
@@ -305,25 +310,32 @@ class Network(nn.Module):
                         res=p0, act_post=ACT_LRELU02)
         affine = self._buf('aa2.aff', (ha, wa, 3), torch.float32)
         self._conv('aa2.align.p_conv.4', p1, None, affine, [(32, 32)], act_post=ACT_CLAMP3, pad=0, bias_add=1.0)
-        out = torch.empty((H2, W2, C), dtype=dt, device=self._device)
         self.ops.aligned_sample(warped, affine, ks, out)
         return out
 
-    def _frame_alignment(self, lr, ref):
+    def _frame_slot(self, slot, h, w):
+        """ring buffers of one frame"""
+        C, dt = self.mid_channels, self.act_dtype
+        r = f'ring{self._b}'
+        return {'conf': self._buf(f'{r}.conf.{slot}', (h, w), torch.float32),
+                'idx': self._buf(f'{r}.idx.{slot}', (h * w,), torch.int32),
+                'aligned': self._buf(f'{r}.al.{slot}', (h, w, C), dt),
+                'aligned_up': self._buf(f'{r}.alup.{slot}', (2 * h, 2 * w, C), dt),
+                'lr8': self._buf(f'{r}.lr8.{slot}', (h, w, 8), dt)}
+
+    def _frame_alignment(self, lr, ref, slot):
         """Everything the RAP module needs from one (LR, Ref) frame pair, all pure functions of the frame
         (RefVSR.py:196-204,233-234 and the aa1 / aa2 calls of RefVSR.py:127,136): matching confidence, the
         reference features gathered at LR resolution (aa1) and gathered + affinely re-sampled at 2x (aa2),
         plus the NHWC copy of the LR frame.  Computed once per frame, reused by every window that contains it."""
-        C, dt = self.mid_channels, self.act_dtype
         h, w = lr.shape[1], lr.shape[2]
-        conf, idx = self._feature_match(lr, ref)
+        fp = self._frame_slot(slot, h, w)
+        self._feature_match(lr, ref, fp['conf'], fp['idx'])
         ref8, ref_feat, ref_feat_down = self._ref_features(ref)
-        aligned = torch.empty((h, w, C), dtype=dt, device=self._device)
-        self.ops.gather_blocks(ref_feat_down, idx, h, w, 1, aligned)     # aa1: scale 1, align=False -> pure gather
-        aligned_up = self._aa2(lr, ref8, idx, ref_feat, h, w)
-        lr8 = torch.empty((h, w, 8), dtype=dt, device=self._device)
-        self.ops.prep_image(lr, lr8)
-        return {'conf': conf, 'idx': idx, 'aligned': aligned, 'aligned_up': aligned_up, 'lr8': lr8}
+        self.ops.gather_blocks(ref_feat_down, fp['idx'], h, w, 1, fp['aligned'])   # aa1: scale 1, align=False
+        self._aa2(lr, ref8, fp['idx'], ref_feat, h, w, fp['aligned_up'])
+        self.ops.prep_image(lr, fp['lr8'])
+        return fp
 
     # ---- RAP module (RefVSR.py:123-149) --------------------------------------------------------------
     def _rap(self, fp, conf_prop, feat_prop, feat_prop_UP, tag):
@@ -383,43 +395,72 @@ class Network(nn.Module):
                         act_pre=ACT_LRELU01, pixel_shuffle=True)
         hr2 = self._conv('conv_hr', hr, None, self._buf('up.hr2', (4 * h, 4 * w, C), dt), [(C, C)], act_pre=ACT_LRELU01)
         last = self._conv('conv_last', hr2, None, self._buf('up.last', (4 * h, 4 * w, 4), torch.float32), [(C, C)])
-        out = torch.empty((3, 4 * h, 4 * w), dtype=torch.float32, device=self._device)
+        out = self._buf('up.out', (3, 4 * h, 4 * w), torch.float32)
         self.ops.reconstruct(last, lr_center, self.scale, clamp01, out)
         return out
 
     # ------------------------------------------------------------------------------------------
-    # per-frame products with exact reuse across sliding windows
+    # per-frame products with exact reuse across sliding windows: plan (pure bookkeeping) + execute
     # ------------------------------------------------------------------------------------------
-    def _frame_products(self, st, lrs, refs, a0, t, need_match_from):
-        """Make sure the per-frame caches hold what this window needs.  Frames are addressed by their
-        absolute index a = a0 + j (a0 = number of calls since the stream started)."""
-        pyr = st['pyr']
-        for k in [k for k in pyr if k < a0]:
-            del pyr[k]
-        for name in ('fw', 'bw', 'frame'):
-            d = st[name]
-            for k in [k for k in d if k < a0]:
-                del d[k]
+    def _plan_products(self, st, a0, t, range_start):
+        """Decide what this window still has to compute and update the bookkeeping.  Frames are addressed by
+        their absolute index a = a0 + j (a0 = calls since the stream started); the product of frame / pair
+        `a` lives in ring slot a % t.  Returns a list of ('pyr'|'fw'|'bw'|'frame', a)."""
+        mid = t // 2
+        for name in ('pyr', 'fw', 'bw', 'frame'):
+            st[name] = {a for a in st[name] if a >= a0}
+        work = []
 
-        def pyramid(j):
-            if a0 + j not in pyr:
-                pyr[a0 + j] = self._pyramid(lrs[j])
-            return pyr[a0 + j]
+        def need_pyr(a):
+            if a not in st['pyr']:
+                st['pyr'].add(a)
+                work.append(('pyr', a))
 
-        h, w = lrs.shape[2], lrs.shape[3]
         ev = _cget(self.config, 'EVAL', None)
         zero_flow = bool(_cget(ev, 'is_gradio', False)) if ev is not None else False   # RefVSR.py:183-191
-        for j in st['need_fw']:          # forward_flows[j] = Flow(lrs[j+1], lrs[j])   (RefVSR.py:182-184)
+        # flows actually consumed by this call (the reference computes all 2(t-1), RefVSR.py:179-193)
+        need_fw = sorted(set(range(range_start, mid)) | ({mid} if mid < t - 1 else set()))
+        need_bw = list(range(mid, t - 1))
+        for j in need_fw:            # forward_flows[j] = Flow(lrs[j+1], lrs[j])   (RefVSR.py:182-184)
             if a0 + j not in st['fw']:
-                st['fw'][a0 + j] = (torch.zeros((h, w, 2), dtype=torch.float32, device=self._device) if zero_flow
-                                    else self._spynet(pyramid(j + 1), pyramid(j), h, w))
-        for j in st['need_bw']:          # backward_flows[j] = Flow(lrs[j], lrs[j+1])  (RefVSR.py:187-189)
+                if not zero_flow:
+                    need_pyr(a0 + j + 1)
+                    need_pyr(a0 + j)
+                st['fw'].add(a0 + j)
+                work.append(('fw0' if zero_flow else 'fw', a0 + j))
+        for j in need_bw:            # backward_flows[j] = Flow(lrs[j], lrs[j+1])  (RefVSR.py:187-189)
             if a0 + j not in st['bw']:
-                st['bw'][a0 + j] = (torch.zeros((h, w, 2), dtype=torch.float32, device=self._device) if zero_flow
-                                    else self._spynet(pyramid(j), pyramid(j + 1), h, w))
-        for j in range(need_match_from, t):
+                if not zero_flow:
+                    need_pyr(a0 + j)
+                    need_pyr(a0 + j + 1)
+                st['bw'].add(a0 + j)
+                work.append(('bw0' if zero_flow else 'bw', a0 + j))
+        for j in range(range_start, t):
             if a0 + j not in st['frame']:
-                st['frame'][a0 + j] = self._frame_alignment(lrs[j], refs[j])
+                st['frame'].add(a0 + j)
+                work.append(('frame', a0 + j))
+        return work
+
+    def _ring(self, kind, a, t, shape, dtype=torch.float32):
+        return self._buf(f'ring{self._b}.{kind}.{a % t}', shape, dtype)
+
+    def _run_products(self, work, t, h, w, hr, wr):
+        for kind, a in work:
+            lr = self._ring('lr32', a, t, (3, h, w))
+            if kind == 'pyr':
+                self._pyramid(lr, a % t)
+            elif kind in ('fw', 'bw'):
+                pa = [self._buf(f'ring{self._b}.pyr{l}.{a % t}', (H, W, 3), torch.float32) for l, (H, W) in enumerate(self._pyr_shapes(h, w))]
+                pb = [self._buf(f'ring{self._b}.pyr{l}.{(a + 1) % t}', (H, W, 3), torch.float32) for l, (H, W) in enumerate(self._pyr_shapes(h, w))]
+                out = self._ring(kind, a, t, (h, w, 2))
+                if kind == 'fw':
+                    self._spynet(pb, pa, out)      # Flow(frame a+1, frame a)
+                else:
+                    self._spynet(pa, pb, out)      # Flow(frame a, frame a+1)
+            elif kind in ('fw0', 'bw0'):
+                self._ring(kind[:2], a, t, (h, w, 2)).zero_()
+            else:
+                self._frame_alignment(lr, self._ring('ref32', a, t, (3, hr, wr)), a % t)
 
     # ------------------------------------------------------------------------------------------
     # forward (RefVSR.py:151-325)
@@ -447,8 +488,8 @@ class Network(nn.Module):
         with torch.no_grad():
             results, vis = [], None
             for b in range(n):
-                res_b, vis_b = self._forward_one(b, lrs[b].float().contiguous(), refs[b].float().contiguous(),
-                                                 bool(is_first_frame), caller_first, bool(is_log), bool(is_train))
+                res_b, vis_b = self._forward_one(b, lrs[b], refs[b], bool(is_first_frame), caller_first,
+                                                 bool(is_log), bool(is_train))
                 results.append(res_b)
                 vis = vis_b if vis is None else vis
             out = torch.stack(results, 0)
@@ -465,17 +506,19 @@ class Network(nn.Module):
         return outs
 
     def _forward_one(self, b, lrs, refs, is_first_frame, caller_first, is_log, is_train):
-        ops = self.ops
-        C, dt = self.mid_channels, self.act_dtype
         t, _, h, w = lrs.shape
+        hr, wr = refs.shape[2], refs.shape[3]
         mid = t // 2
+        self._b = b           # ring / state namespace of this batch element
 
         # stream bookkeeping for exact reuse: a caller-declared first frame starts a new stream; forced
         # resets (reset_branch) keep sliding, so the caches stay valid across them.
         st = self._state.get(b)
-        if st is None or caller_first or not self.reuse or is_train or st.get('shape') != (t, h, w, refs.shape[2], refs.shape[3]):
-            st = {'a0': 0, 'pyr': {}, 'fw': {}, 'bw': {}, 'frame': {}, 'prev': st.get('prev') if st else None,
-                  'shape': (t, h, w, refs.shape[2], refs.shape[3])}
+        shape = (t, h, w, hr, wr)
+        fresh = (st is None or caller_first or not self.reuse or is_train or st.get('shape') != shape)
+        if fresh:
+            st = {'a0': 0, 'pyr': set(), 'fw': set(), 'bw': set(), 'frame': set(), 'staged': set(),
+                  'has_prev': bool(st and st.get('has_prev')) and st.get('shape') == shape, 'shape': shape}
             self._state[b] = st
         else:
             st['a0'] += 1
@@ -485,15 +528,54 @@ class Network(nn.Module):
             range_start = 0
         else:
             range_start = mid if not is_train else 0                          # RefVSR.py:173-176
-            if st['prev'] is None:
+            if not st['has_prev']:
                 raise RuntimeError('is_first_frame=False but no propagated state exists '
                                    '(the reference fails the same way: RefVSR.py:256-260)')
-        # flows actually consumed by this call (the reference computes all 2(t-1), RefVSR.py:179-193)
-        st['need_bw'] = list(range(mid, t - 1))
-        st['need_fw'] = sorted(set(range(range_start, mid)) | ({mid} if mid < t - 1 else set()))
-        self._frame_products(st, lrs, refs, a0, t, range_start)
 
+        # stage the frames that entered the window into their ring slots (fp32 copies; outside any graph)
+        st['staged'] = {a for a in st['staged'] if a >= a0}
+        for j in range(t):
+            if a0 + j not in st['staged']:
+                self._ring('lr32', a0 + j, t, (3, h, w)).copy_(lrs[j])
+                self._ring('ref32', a0 + j, t, (3, hr, wr)).copy_(refs[j])
+                st['staged'].add(a0 + j)
+
+        work = self._plan_products(st, a0, t, range_start)
+        variant = 'first' if is_first_frame else 'steady'
+        args = (b, st, a0, t, h, w, hr, wr, work, is_first_frame, range_start, is_log, is_train)
+        use_graph = (self.use_graphs and not fresh and not is_log and not is_train and lrs.is_cuda
+                     and hasattr(torch.cuda, 'CUDAGraph'))
+        if use_graph:
+            key = (b, shape, a0 % t, variant, tuple((k, a - a0) for k, a in work))
+            entry = self._graphs.get(key)
+            if entry is None:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out_static, _ = self._run_window(*args)
+                entry = (graph, out_static)
+                self._graphs[key] = entry
+            entry[0].replay()
+            out, vis = entry[1].clone(), None
+        else:
+            out_static, vis = self._run_window(*args)
+            out = out_static.clone()
+        st['has_prev'] = True
+        return out, vis
+
+    def _run_window(self, b, st, a0, t, h, w, hr, wr, work, is_first_frame, range_start, is_log, is_train):
+        """All kernel launches of one window.  Reads / writes static buffers only (graph-capturable)."""
+        ops = self.ops
+        C, dt = self.mid_channels, self.act_dtype
+        mid = t // 2
+        self._run_products(work, t, h, w, hr, wr)
         vis = {'vis': collections.OrderedDict()} if is_log else None
+
+        def frame(i):
+            return self._frame_slot((a0 + i) % t, h, w)
+
+        def lr32(i):
+            return self._ring('lr32', a0 + i, t, (3, h, w))
 
         # ---------------- backward branch (RefVSR.py:211-238) ----------------
         feat_prop = self._buf('bw.z.feat', (h, w, C), dt).zero_()
@@ -501,7 +583,7 @@ class Network(nn.Module):
         conf_prop = self._buf('bw.z.conf', (h, w), torch.float32).zero_()
         for i in range(t - 1, mid - 1, -1):
             if i < t - 1:
-                flow = st['bw'][a0 + i]
+                flow = self._ring('bw', a0 + i, t, (h, w, 2))
                 wf = self._buf('bw.w.feat', (h, w, C), dt)
                 ops.warp(feat_prop, flow, wf)
                 wc = self._buf('bw.w.conf', (h, w), torch.float32)
@@ -510,8 +592,8 @@ class Network(nn.Module):
                 ops.warp(feat_prop_UP, flow, wu, flow_up2=True)                # RefVSR.py:220
                 feat_prop, conf_prop, feat_prop_UP = wf, wc, wu
                 if is_log and i == mid:
-                    vis['vis']['BW_LR_next_warp'] = self._warp_image(lrs[i + 1], flow)
-            fp = st['frame'][a0 + i]
+                    vis['vis']['BW_LR_next_warp'] = self._warp_image(lr32(i + 1), flow)
+            fp = frame(i)
             agg = self._prop_resblocks('backward_resblocks', fp['lr8'], feat_prop,
                                        self._buf('bw.agg', (h, w, C), dt), 'bw.rb')
             feat_prop, feat_prop_UP, conf_prop = self._rap(fp, conf_prop, agg, feat_prop_UP, f'bw.rap{i % 2}')
@@ -524,10 +606,12 @@ class Network(nn.Module):
             feat_prop_UP = self._buf('fw.z.featUP', (2 * h, 2 * w, C), dt).zero_()
             conf_prop = self._buf('fw.z.conf', (h, w), torch.float32).zero_()
             range_start = 0
+        prev = {'feat': self._buf(f'prev{b}.feat', (h, w, C), dt), 'featUP': self._buf(f'prev{b}.featUP', (2 * h, 2 * w, C), dt),
+                'conf': self._buf(f'prev{b}.conf', (h, w), torch.float32), 'flow': self._buf(f'prev{b}.flow', (h, w, 2), torch.float32)}
         flow = None
         for i in range(range_start, mid + 1):
             if i > range_start:
-                flow = st['fw'][a0 + i - 1]
+                flow = self._ring('fw', a0 + i - 1, t, (h, w, 2))
                 wf = self._buf('fw.w.feat', (h, w, C), dt)
                 ops.warp(feat_prop, flow, wf)
                 # quirk kept on purpose: the LR-resolution feat_prop (already warped once) is warped onto
@@ -538,7 +622,6 @@ class Network(nn.Module):
                 ops.warp(conf_prop, flow, wc)
                 feat_prop, feat_prop_UP, conf_prop = wf, wu, wc
             elif i == range_start and not is_first_frame:
-                prev = st['prev']
                 flow = prev['flow']
                 wf = self._buf('fw.w.feat', (h, w, C), dt)
                 ops.warp(prev['feat'], flow, wf)
@@ -548,21 +631,24 @@ class Network(nn.Module):
                 ops.warp(prev['conf'], flow, wc)
                 feat_prop, feat_prop_UP, conf_prop = wf, wu, wc
             if is_log and i == mid and flow is not None:
-                vis['vis']['FW_LR_prev_warp'] = self._warp_image(lrs[i - 1], flow)
-            fp = st['frame'][a0 + i]
+                vis['vis']['FW_LR_prev_warp'] = self._warp_image(lr32(i - 1), flow)
+            fp = frame(i)
             agg = self._prop_resblocks('forward_resblocks', fp['lr8'], feat_prop,
                                        self._buf('fw.agg', (h, w, C), dt), 'fw.rb')
             feat_prop, feat_prop_UP, conf_prop = self._rap(fp, conf_prop, agg, feat_prop_UP, f'fw.rap{i % 2}')
             if (is_train and i == 0) or (not is_train and i == mid):           # RefVSR.py:279-283
-                st['prev'] = {'feat': feat_prop.clone(), 'featUP': feat_prop_UP.clone(), 'conf': conf_prop.clone(),
-                              'flow': st['fw'][a0 + i].clone() if (a0 + i) in st['fw'] else None}
+                prev['feat'].copy_(feat_prop)
+                prev['featUP'].copy_(feat_prop_UP)
+                prev['conf'].copy_(conf_prop)
+                if (a0 + i) in st['fw']:
+                    prev['flow'].copy_(self._ring('fw', a0 + i, t, (h, w, 2)))
 
         # ---------------- U (RefVSR.py:286-297) ----------------
-        out = self._compute_up(backward_feat_UP, feat_prop_UP, conf_bw, conf_prop, lrs[mid], clamp01=not is_train)
+        out = self._compute_up(backward_feat_UP, feat_prop_UP, conf_bw, conf_prop, lr32(mid), clamp01=not is_train)
 
         if is_log and _cget(self.config, 'save_sample', False):
             ev = collections.OrderedDict()
-            ev['conf_map'] = st['frame'][a0 + mid]['conf'].view(1, 1, h, w).clone()
+            ev['conf_map'] = frame(mid)['conf'].view(1, 1, h, w).clone()
             ev['conf_map_prop_backward'] = conf_bw.view(1, 1, h, w).clone()
             ev['conf_map_prop_forward'] = conf_prop.view(1, 1, h, w).clone()
             ev['conf_map_prop'] = torch.maximum(ev['conf_map_prop_backward'], ev['conf_map_prop_forward'])

@@ -69,6 +69,27 @@ def test_reuse_is_exact():
         assert torch.equal(a, b)
 
 
+def test_cuda_graphs_are_exact():
+    """whole-window CUDA graphs (one launch per window after first occurrence) vs eager launches: bit identical,
+    across steady windows, ring wrap-around and forced resets (reset_branch)."""
+    from refvsr_b200 import SRNet, get_config
+    from refvsr_b200.modules import seeded_test_weights
+    from refvsr_b200.synth import make_clip, sliding_windows
+    lrs, refs = make_clip(24, 24, 32, 1, seed=7)
+    res = {}
+    for graphs in (True, False):
+        cfg = get_config('RefVSR_small_MFID', device='cuda', num_blocks=2, b200_precision='fp16', b200_cuda_graphs=graphs)
+        net = SRNet(cfg).eval()
+        seeded_test_weights(net, seed=7)
+        net = net.cuda()
+        res[graphs] = [net(wl.cuda(), wr.cuda(), first, False, False)['result'].cpu()
+                       for k, wl, wr, first in sliding_windows(lrs, refs, 7)]
+        if graphs:
+            assert len(net.Network._graphs) >= 8, 'graphs must actually have been captured'
+    for k, (a, b) in enumerate(zip(res[True], res[False])):
+        assert torch.equal(a, b), f'window {k}: graph replay differs from eager'
+
+
 def test_medium_size_against_oracle():
     """96x128 LR, RefVSR_small_MFID with all 24 blocks, 3 windows: CUDA fp32 path vs the CPU oracle."""
     from oracle.refvsr_oracle import OracleRefVSR
