@@ -87,6 +87,8 @@ typedef struct rv_conv_desc {
   int32_t impl;          /* RV_CONV_IMPL_*                                                */
   int32_t nb;            /* TC: output channels per CTA column block (packing.py decides) */
   int32_t k_real;        /* SIMT: rows of wpack = kh*kw*(c0+c1)                           */
+  int32_t layout;        /* TC: 0 = [nblk][kx][chunk][ky][NB][64] (one TMA box per kx),    */
+                         /*     1 = [nblk][chunk][ky][kx][NB][64] (one box per tile+chunk) */
 } rv_conv_desc;
 
 int rv_conv2d(const rv_conv_desc* d, void* stream);

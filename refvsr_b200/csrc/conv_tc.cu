@@ -19,6 +19,8 @@
 // four warps; group g drains accumulator buffer g (tiles of parity g), so two tiles are in their epilogue
 // at any time while the MMA warp fills the next one (tcgen05.ld -> bias/act/gate/residual -> NHWC or
 // pixel-shuffled store).  The epilogue math is branch-free and fully unrolled (registers only).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -26,6 +28,7 @@ namespace rv {
 
 static constexpr int TH = 8, TW = 16;
 static constexpr int MAX_SLOTS = 8;
+static constexpr int NACC = 3;  // TMEM accumulator buffers == epilogue warp groups
 
 struct TcP {
   int Ho, Wo, kh, kw, pad;
@@ -43,6 +46,10 @@ struct TcP {
   void* out;
   int out_cs, pixel_shuffle, fmt, vec_ok;
   uint32_t tmem_cols, acc_stride;
+  // tile geometry: mode 0 = 8 rows x 16 cols, one box per (kx, chunk) stage (y-halo only);
+  //                mode 1 = 16 rows x 8 cols, ONE box per (chunk) stage with x- and y-halo, taps = shifted views
+  int single_box, th, tw, tw_shift, bw;   // bw = box width in pixels (mode 1: 8 or 16)
+  int bo_force;                           // experiment hook: constant base_offset for kx != 0 taps (-1 = kx)
 };
 
 template <typename T>
@@ -103,12 +110,39 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint64_t ad, uint64_
   }
 }
 
+// mode 1: all KH x KW taps of one channel chunk read the same box.  Tap (ky,kx) starts (ky*bw + kx) pixel
+// rows (128 B each) into the box; 8-row groups of the M dimension are bw rows apart (SBO).  The start is
+// then not 1024-byte aligned, which is fine: see the base_offset note below.
+template <int KH>
+__device__ __forceinline__ void issue_taps_box(uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t idesc, int ksteps,
+                                               uint32_t b_tap, int bw, int bo_force, uint32_t& accumulate) {
+#pragma unroll
+  for (int ky = 0; ky < KH; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < KH; ++kx) {
+      // base_offset (bits [49,52)) stays 0: measured on B200, the operand swizzle is a pure function of the
+      // absolute shared-memory address bits, so a view that starts kx rows into a 1024-byte atom reads exactly
+      // what TMA wrote; a non-zero base_offset shifts the XOR phase and corrupts the operand (experiment hook).
+      const int bo = (bo_force >= 0 && kx != 0) ? bo_force : 0;
+      const uint64_t a_tap = ad + (uint64_t)((ky * bw + kx) * 8) + ((uint64_t)bo << 49);
+      const uint64_t b_t = bd + (uint64_t)((ky * KH + kx) * b_tap);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < ksteps) {
+          tc::umma_f16(d_tmem, a_tap + (uint64_t)(k * 2), b_t + (uint64_t)(k * 2), idesc, accumulate);
+          accumulate = 1;
+        }
+      }
+    }
+  }
+}
+
 template <typename TI, typename TR, typename TO>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(64 + 128 * NACC, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                const TcP p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_full[MAX_SLOTS], bar_empty[MAX_SLOTS], bar_w, bar_tfull[2], bar_tempty[2];
+  __shared__ uint64_t bar_full[MAX_SLOTS], bar_empty[MAX_SLOTS], bar_w, bar_tfull[NACC], bar_tempty[NACC];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[256];
 
@@ -128,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       tc::mbar_init(&bar_empty[i], 1);
     }
     tc::mbar_init(&bar_w, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NACC; ++i) {
       tc::mbar_init(&bar_tfull[i], 1);
       tc::mbar_init(&bar_tempty[i], 4);
     }
@@ -161,7 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       int ty0 = blockIdx.x / p.tiles_x, tx0 = blockIdx.x - ty0 * p.tiles_x;   // tile coordinates, advanced incrementally
       const int dty = gridDim.x / p.tiles_x, dtx = gridDim.x - dty * p.tiles_x;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int yc = ty0 * TH - p.pad, xc = tx0 * TW - p.pad;
+        const int yc = ty0 * p.th - p.pad, xc = tx0 * p.tw - p.pad;
         int kx = 0, ch = 0;
         for (int s = 0; s < p.S; ++s) {
           tc::mbar_wait(&bar_empty[slot], ph ^ 1u);
@@ -173,7 +207,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
             tc::tma_load_3d(&tm1, &bar_full[slot], dstA, (ch - p.nch0) * 64, xc + kx, yc);
           if (!p.resident)
             tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_full[slot], smemW + (size_t)slot * p.w_bytes, p.w_bytes);
-          if (++ch == nchunks) { ch = 0; ++kx; }
+          if (++ch == nchunks) { ch = 0; kx += p.single_box ? 0 : 1; }
           if (++slot == p.slots) { slot = 0; ph ^= 1u; }
         }
         tx0 += dtx; ty0 += dty;
@@ -186,14 +220,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     // descriptors are 64-bit bases plus small immediates, the tap loop is unrolled per kernel height.
     if (lane == 0) {
       const uint32_t idesc = tc::umma_idesc(p.fmt, 128, p.NB);
-      const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(smemA));
+      // SBO (bits [32,46)): 1024 B between 8-row groups in mode 0, bw*128 B (next tile row) in mode 1
+      const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(smemA)) +
+                              (p.single_box ? ((uint64_t)((p.bw * 128 - 1024) >> 4) << 32) : 0ull);
       const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(smemW));
       const uint32_t a_step = p.a_bytes >> 4, w_step = p.w_bytes >> 4, b_tap = (uint32_t)(p.NB * 128) >> 4;
       if (p.resident) tc::mbar_wait(&bar_w, 0);
       int slot = 0;
-      uint32_t ph = 0, t = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
-        const uint32_t acc = t & 1u, accph = (t >> 1) & 1u;
+      uint32_t ph = 0, acc = 0, accph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         tc::mbar_wait(&bar_tempty[acc], accph ^ 1u);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
@@ -206,6 +241,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)(p.resident ? s : slot) * w_step);
           tc::mbar_wait(&bar_full[slot], ph);
           tc::tc_fence_after();
+          if (p.single_box) {
+            switch (p.kh) {
+              case 1: issue_taps_box<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
+              case 3: issue_taps_box<3>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
+              case 5: issue_taps_box<5>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
+              default: issue_taps_box<7>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
+            }
+          } else
           switch (p.kh) {
             case 1: issue_taps<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
             case 3: issue_taps<3>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
@@ -223,6 +266,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           if (++slot == p.slots) { slot = 0; ph ^= 1u; }
         }
         tc::umma_commit(&bar_tfull[acc]);
+        if (++acc == NACC) { acc = 0; accph ^= 1u; }
       }
     }
   } else {
@@ -230,17 +274,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     const int grp = (warp - 2) >> 2;  // accumulator buffer / tile parity owned by this group
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
-    const int ty = m / TW, tx = m % TW;
+    const int ty = m >> p.tw_shift, tx = m & (p.tw - 1);
     const TI* gate = reinterpret_cast<const TI*>(p.gate);
     const TR* res = reinterpret_cast<const TR*>(p.res);
     TO* out = reinterpret_cast<TO*>(p.out);
     const float pre_slope = p.pre_slope, post_slope = p.post_slope;
-    uint32_t t = 0;
-    constexpr int PRE = 4;  // chunks whose residual / gate vectors are prefetched before the accumulator wait
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
-      if ((int)(t & 1u) != grp) continue;
-      const uint32_t acc = t & 1u, accph = (t >> 1) & 1u;
-      const int oy = (tile / p.tiles_x) * TH + ty, ox = (tile % p.tiles_x) * TW + tx;
+    constexpr int PRE = 3;  // chunks whose residual / gate vectors are prefetched before the accumulator wait
+    const uint32_t acc = (uint32_t)grp;
+    uint32_t accph = 0;
+    // group g owns accumulator g: tiles blockIdx.x + (g + NACC*i) * gridDim.x
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += NACC * gridDim.x, accph ^= 1u) {
+      const int oy = (tile / p.tiles_x) * p.th + ty, ox = (tile % p.tiles_x) * p.tw + tx;
       const bool valid = (oy < p.Ho) && (ox < p.Wo);
       const size_t pix = (size_t)oy * p.Wo + ox;
       // ---- prefetch: one DRAM round trip per tile, overlapped with the MMAs of this tile ----
@@ -306,10 +350,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float x = __uint_as_float(r[j]) + bias_s[c0 + j];
-          x = x > 0.f ? x : x * pre_slope;
+          x = fmaxf(x, x * pre_slope);      // slope in [0,1]: identity / ReLU / LeakyReLU without a select
           if (gate) x *= g[j];
           if (res) x += rr[j];
-          x = x > 0.f ? x : x * post_slope;
+          x = fmaxf(x, x * post_slope);
           v[j] = x;
         }
         if (p.post_clamp3) {
@@ -367,12 +411,12 @@ PFN_tmapEncodeTiled get_tmap_encoder() {
   return fn;
 }
 
-static int make_act_tmap(CUtensorMap* m, const void* ptr, int C, int W, int H, int box_rows, int fmt) {
+static int make_act_tmap(CUtensorMap* m, const void* ptr, int C, int W, int H, int box_w, int box_rows, int fmt) {
   PFN_tmapEncodeTiled enc = get_tmap_encoder();
   if (!enc) return fail(RV_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H};
   cuuint64_t gstr[2] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)TW, (cuuint32_t)box_rows};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_w, (cuuint32_t)box_rows};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
                    const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -394,7 +438,7 @@ static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& 
     RV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  kern<<<grid, 320, smem, st>>>(tm0, tm1, p);
+  kern<<<grid, 64 + 128 * NACC, smem, st>>>(tm0, tm1, p);
   RV_LAUNCH_CHECK("conv_tc");
   return RV_OK;
 }
@@ -421,16 +465,33 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   p.kh = d->kh; p.kw = d->kw; p.pad = d->pad;
   p.c0 = d->c0; p.c1 = d->src1 ? d->c1 : 0;
   p.nch0 = (p.c0 + 63) / 64; p.nch1 = (p.c1 + 63) / 64;
-  p.S = d->kw * (p.nch0 + p.nch1);
   p.NB = d->nb; p.cout = d->cout;
-  p.tiles_x = (p.Wo + TW - 1) / TW; p.tiles_y = (p.Ho + TH - 1) / TH;
-  p.a_bytes = (uint32_t)(TH + d->kh - 1) * TW * 128;
-  p.w_bytes = (uint32_t)d->kh * p.NB * 128;
   const int nblk = (d->cout + p.NB - 1) / p.NB;
-  // shared-memory plan: weights resident when they leave room for >= 3 A slots
   const size_t budget = (size_t)g_max_smem - 1024 /*alignment*/ - 4096 /*static: barriers, bias*/;
+  // mode 1 (single box per tile and chunk) when the whole weight set stays resident next to >= 2 boxes
+  p.single_box = 0;
+  if (d->layout == 1) {
+    RV_REQUIRE(d->kh == d->kw && (d->kh == 1 || d->kh == 3 || d->kh == 5 || d->kh == 7), "rv_conv2d(tc): layout 1 needs a square 1/3/5/7 kernel");
+    p.single_box = 1;
+  }
+  if (p.single_box) {
+    p.th = 16; p.tw = 8; p.tw_shift = 3;
+    p.bw = (d->kw == 1) ? 8 : 16;
+    p.S = p.nch0 + p.nch1;
+    p.a_bytes = (uint32_t)(p.th + d->kh - 1) * p.bw * 128;
+    p.w_bytes = (uint32_t)d->kh * d->kw * p.NB * 128;
+    RV_REQUIRE((size_t)p.S * p.w_bytes + 2 * (size_t)p.a_bytes <= budget, "rv_conv2d(tc): layout 1 weights do not fit in shared memory");
+  } else {
+    p.th = TH; p.tw = TW; p.tw_shift = 4; p.bw = TW;
+    p.S = d->kw * (p.nch0 + p.nch1);
+    p.a_bytes = (uint32_t)(TH + d->kh - 1) * TW * 128;
+    p.w_bytes = (uint32_t)d->kh * p.NB * 128;
+  }
+  { const char* e = getenv("REFVSR_BO_FORCE"); p.bo_force = e ? atoi(e) : -1; }
+  p.tiles_x = (p.Wo + p.tw - 1) / p.tw; p.tiles_y = (p.Ho + p.th - 1) / p.th;
+  // shared-memory plan: weights resident when they leave room for >= 3 A slots
   const size_t w_all = (size_t)p.S * p.w_bytes;
-  if (w_all + 3 * (size_t)p.a_bytes <= budget) {
+  if (p.single_box || w_all + 3 * (size_t)p.a_bytes <= budget) {
     p.resident = 1;
     p.slots = (int)std::min<size_t>(MAX_SLOTS, (budget - w_all) / p.a_bytes);
   } else {
@@ -439,7 +500,7 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
     RV_REQUIRE(p.slots >= 2, "rv_conv2d(tc): stage of %u bytes does not fit twice in shared memory",
                p.a_bytes + p.w_bytes);
   }
-  p.slots = std::min(p.slots, std::max(2, 2 * p.S));
+  p.slots = std::min(p.slots, std::max(2, p.single_box ? 6 * p.S : 3 * p.S));
   const size_t smem = 1024 + (size_t)p.slots * p.a_bytes + (p.resident ? w_all : (size_t)p.slots * p.w_bytes);
   p.wpack = (const uint8_t*)d->wpack; p.bias = d->bias;
   auto slope = [](int act) { return act == RV_ACT_RELU ? 0.f : act == RV_ACT_LRELU01 ? 0.1f : act == RV_ACT_LRELU02 ? 0.2f : 1.f; };
@@ -454,14 +515,14 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   p.vec_ok = al16(d->out, d->out_cs, d->out_dtype) && al16(d->gate, d->gate_cs, d->in_dtype) && al16(d->res, d->res_cs, rdt);
   p.acc_stride = (uint32_t)p.NB;
   uint32_t cols = 32;
-  while (cols < 2u * p.NB) cols <<= 1;
+  while (cols < (uint32_t)NACC * p.NB) cols <<= 1;
   p.tmem_cols = cols;
 
   CUtensorMap tm0, tm1;
-  int rc = make_act_tmap(&tm0, d->src0, p.c0, d->W, d->H, TH + d->kh - 1, p.fmt);
+  int rc = make_act_tmap(&tm0, d->src0, p.c0, d->W, d->H, p.bw, p.th + d->kh - 1, p.fmt);
   if (rc) return rc;
   if (p.nch1) {
-    rc = make_act_tmap(&tm1, d->src1, p.c1, d->W, d->H, TH + d->kh - 1, p.fmt);
+    rc = make_act_tmap(&tm1, d->src1, p.c1, d->W, d->H, p.bw, p.th + d->kh - 1, p.fmt);
     if (rc) return rc;
   } else {
     tm1 = tm0;

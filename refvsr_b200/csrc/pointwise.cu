@@ -288,6 +288,76 @@ __global__ void warp_kernel(const T* __restrict__ src, int Hi, int Wi, int C,
   stv<T, V>(out + (size_t)p * C + (size_t)vc * V, o);
 }
 
+// Vector variant used for feature maps: phase 1 computes, once per output pixel, the four corner
+// offsets (clamped) and weights (zeroed when the corner is outside the image) into shared memory;
+// phase 2 is a branch-free 4-tap gather with one thread per (pixel, 16-byte channel vector), so global
+// loads and stores stay fully coalesced along the NHWC channel axis.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) warp_vec_kernel(const T* __restrict__ src, int Hi, int Wi, int C,
+                                                       const float* __restrict__ flow, int hf, int wf,
+                                                       int flow_up2, T* __restrict__ out, int ppb) {
+  __shared__ float4 s_w[256];
+  __shared__ int4 s_o[256];
+  const int Ho = flow_up2 ? 2 * hf : hf, Wo = flow_up2 ? 2 * wf : wf;
+  const int cv = C / V;
+  const int npix = Ho * Wo;
+  const int p0 = blockIdx.x * ppb;
+  if (threadIdx.x < ppb && p0 + threadIdx.x < npix) {
+    const int p = p0 + threadIdx.x;
+    const int Y = p / Wo, X = p - Y * Wo;
+    float fx, fy;
+    if (flow_up2) {
+      int y0, y1, x0, x1;
+      float ly, lx;
+      float sy = (Ho > 1) ? (float)(hf - 1) / (float)(Ho - 1) : 0.f;
+      float sx = (Wo > 1) ? (float)(wf - 1) / (float)(Wo - 1) : 0.f;
+      bilin_src_ac(Y, sy, hf, y0, y1, ly);
+      bilin_src_ac(X, sx, wf, x0, x1, lx);
+      float hy = 1.f - ly, hx = 1.f - lx;
+      const float2* f2 = reinterpret_cast<const float2*>(flow);
+      float2 a = __ldg(f2 + y0 * wf + x0), b = __ldg(f2 + y0 * wf + x1), c = __ldg(f2 + y1 * wf + x0),
+             d = __ldg(f2 + y1 * wf + x1);
+      fx = (hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x)) * 2.0f;
+      fy = (hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y)) * 2.0f;
+    } else {
+      float2 f = __ldg(reinterpret_cast<const float2*>(flow) + p);
+      fx = f.x;
+      fy = f.y;
+    }
+    float gx = linspace_m1_1(X, Wo) + fx / (((float)Wi - 1.0f) / 2.0f);   // models/utils.py:36-43
+    float gy = linspace_m1_1(Y, Ho) + fy / (((float)Hi - 1.0f) / 2.0f);
+    float px = ((gx + 1.f) * (float)Wi - 1.f) / 2.f;
+    float py = ((gy + 1.f) * (float)Hi - 1.f) / 2.f;
+    float xw = floorf(px), yn = floorf(py);
+    int ix = (int)xw, iy = (int)yn;
+    float xe = xw + 1.f, ys = yn + 1.f;
+    float4 wq = make_float4((xe - px) * (ys - py), (px - xw) * (ys - py), (xe - px) * (py - yn), (px - xw) * (py - yn));
+    const bool x0ok = ix >= 0 && ix < Wi, x1ok = ix + 1 >= 0 && ix + 1 < Wi;
+    const bool y0ok = iy >= 0 && iy < Hi, y1ok = iy + 1 >= 0 && iy + 1 < Hi;
+    if (!(y0ok && x0ok)) wq.x = 0.f;
+    if (!(y0ok && x1ok)) wq.y = 0.f;
+    if (!(y1ok && x0ok)) wq.z = 0.f;
+    if (!(y1ok && x1ok)) wq.w = 0.f;
+    const int cx0 = clampi(ix, 0, Wi - 1), cx1 = clampi(ix + 1, 0, Wi - 1);
+    const int cy0 = clampi(iy, 0, Hi - 1), cy1 = clampi(iy + 1, 0, Hi - 1);
+    s_w[threadIdx.x] = wq;
+    s_o[threadIdx.x] = make_int4(cy0 * Wi + cx0, cy0 * Wi + cx1, cy1 * Wi + cx0, cy1 * Wi + cx1);
+  }
+  __syncthreads();
+  const int pl = threadIdx.x / cv, vc = threadIdx.x - pl * cv;
+  if (pl >= ppb || p0 + pl >= npix) return;
+  const float4 wq = s_w[pl];
+  const int4 o = s_o[pl];
+  const T* base = src + (size_t)vc * V;
+  Vec<T, V> t0 = ldv<T, V>(base + (size_t)o.x * C), t1 = ldv<T, V>(base + (size_t)o.y * C),
+            t2 = ldv<T, V>(base + (size_t)o.z * C), t3 = ldv<T, V>(base + (size_t)o.w * C);
+  Vec<T, V> r;
+#pragma unroll
+  for (int k = 0; k < V; ++k)
+    r.v[k] = from_f<T>(to_f(t0.v[k]) * wq.x + to_f(t1.v[k]) * wq.y + to_f(t2.v[k]) * wq.z + to_f(t3.v[k]) * wq.w);
+  stv<T, V>(out + (size_t)(p0 + pl) * C + (size_t)vc * V, r);
+}
+
 // ---------------------------------------------------------------------------------------------
 // rv_patch_pack : one warp per pixel
 // ---------------------------------------------------------------------------------------------
@@ -564,9 +634,9 @@ static int warp_launch(const void* src, int Hi, int Wi, int C, const float* flow
   constexpr int VMAX = 16 / sizeof(T);
   long long px = (long long)(up2 ? 4 : 1) * hf * wf;
   bool aligned = ((uintptr_t)src % 16 == 0) && ((uintptr_t)out % 16 == 0);
-  if (C % VMAX == 0 && aligned) {
-    long long n = px * (C / VMAX);
-    warp_kernel<T, VMAX><<<cdiv(n, 256), 256, 0, st>>>((const T*)src, Hi, Wi, C, flow, hf, wf, up2, (T*)out);
+  if (C % VMAX == 0 && aligned && C / VMAX <= 256) {
+    const int cv = C / VMAX, ppb = 256 / cv;   // pixels per block
+    warp_vec_kernel<T, VMAX><<<cdiv(px, ppb), 256, 0, st>>>((const T*)src, Hi, Wi, C, flow, hf, wf, up2, (T*)out, ppb);
   } else {
     long long n = px * C;
     warp_kernel<T, 1><<<cdiv(n, 256), 256, 0, st>>>((const T*)src, Hi, Wi, C, flow, hf, wf, up2, (T*)out);

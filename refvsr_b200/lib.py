@@ -31,6 +31,7 @@ class rv_conv_desc(C.Structure):
         ('res', C.c_void_p), ('res_cs', C.c_int32), ('res_dtype', C.c_int32),
         ('out', C.c_void_p), ('out_cs', C.c_int32), ('out_dtype', C.c_int32),
         ('pixel_shuffle', C.c_int32), ('impl', C.c_int32), ('nb', C.c_int32), ('k_real', C.c_int32),
+        ('layout', C.c_int32),
     ]
 
 
@@ -147,6 +148,7 @@ class CudaOps:
         d.impl = layer.impl
         d.nb = layer.nb
         d.k_real = layer.k_real
+        d.layout = getattr(layer, 'layout', 0)
         _check(self.lib, self.lib.rv_conv2d(C.byref(d), self._stream()), f'rv_conv2d[{layer.name}]')
 
     def space_to_depth2(self, src, out):

@@ -30,6 +30,7 @@ class PackedConv:
     k_real: int
     wpack: torch.Tensor
     bias: torch.Tensor
+    layout: int = 0
 
 
 def _expand_inputs(weight, srcs):
@@ -91,7 +92,7 @@ def choose_nb(cout):
     return 64
 
 
-def pack_tc(weight, srcs, dtype, nb):
+def pack_tc(weight, srcs, dtype, nb, layout=0):
     cout, _, kh, kw = weight.shape
     w = weight.float()
     nblk = (cout + nb - 1) // nb
@@ -113,17 +114,39 @@ def pack_tc(weight, srcs, dtype, nb):
     wc = torch.stack(chunks, 0)                               # (nchunks, cout, 64, kh, kw)
     wpad = w.new_zeros(nchunks, nblk * nb, 64, kh, kw)
     wpad[:, :cout] = wc
-    # -> [nblk][kx][chunk][ky][n][c]
-    t = wpad.view(nchunks, nblk, nb, 64, kh, kw).permute(1, 5, 0, 4, 2, 3).contiguous()
-    t = t.view(nblk, S, kh, nb, 8, 8)                         # 64 channels = 8 chunks x 8 elements
+    if layout == 1:   # [nblk][chunk][ky][kx][n][c]: one stage per chunk holding all kh*kw taps
+        S, kh_eff = nchunks, kh * kw
+        t = wpad.view(nchunks, nblk, nb, 64, kh, kw).permute(1, 0, 4, 5, 2, 3).contiguous()
+    else:             # [nblk][kx][chunk][ky][n][c]
+        kh_eff = kh
+        t = wpad.view(nchunks, nblk, nb, 64, kh, kw).permute(1, 5, 0, 4, 2, 3).contiguous()
+    t = t.view(nblk, S, kh_eff, nb, 8, 8)                     # 64 channels = 8 chunks x 8 elements
     out = torch.empty_like(t)
     ar = torch.arange(8, device=t.device)
     for m in range(8):
         out[:, :, :, m::8] = t[:, :, :, m::8][..., ar ^ m, :]
-    return out.view(nblk, S, kh, nb, 64).to(dtype).contiguous()
+    return out.view(nblk, S, kh_eff, nb, 64).to(dtype).contiguous()
 
 
-def pack_conv(name, weight, bias, srcs, stride, pad, act_dtype, device, prefer_tc=True, bias_add=0.0):
+SMEM_BUDGET = 232448 - 1024 - 4096      # opt-in shared memory per CTA minus alignment and static (conv_tc.cu)
+
+
+def choose_layout(kh, kw, srcs, nb):
+    """layout 1 (one TMA box per tile and channel chunk, taps as shifted descriptor views) whenever all taps of
+    all chunks stay resident in shared memory next to >= 3 activation boxes; otherwise layout 0."""
+    import os
+    forced = os.environ.get('REFVSR_TC_LAYOUT')
+    if forced is not None:
+        return int(forced) if (int(forced) == 0 or (kh == kw and kh in (1, 3, 5, 7))) else 0
+    if kh != kw or kh not in (1, 3, 5, 7):
+        return 0
+    nchunks = sum((a + 63) // 64 for _, a in srcs)
+    w_all = nchunks * kh * kw * nb * 128
+    a_bytes = (16 + kh - 1) * (8 if kw == 1 else 16) * 128
+    return 1 if w_all + 3 * a_bytes <= SMEM_BUDGET else 0
+
+
+def pack_conv(name, weight, bias, srcs, stride, pad, act_dtype, device, prefer_tc=True, bias_add=0.0, tc_layout=None):
     """Pick the implementation and build the packed tensors.  `srcs` = [(real, alloc), ...] (1 or 2)."""
     cout, _, kh, kw = weight.shape
     alloc0 = srcs[0][1]
@@ -133,9 +156,10 @@ def pack_conv(name, weight, bias, srcs, stride, pad, act_dtype, device, prefer_t
     b = bias.detach().float() + bias_add
     if tc_ok:
         nb = choose_nb(cout)
-        wp = pack_tc(weight.detach(), srcs, act_dtype, nb).to(device)
+        layout = choose_layout(kh, kw, srcs, nb) if tc_layout is None else tc_layout
+        wp = pack_tc(weight.detach(), srcs, act_dtype, nb, layout).to(device)
         return PackedConv(name, cout, kh, kw, stride, pad, alloc0, alloc1, IMPL_TC, nb,
-                          kh * kw * (alloc0 + alloc1), wp, b.to(device).contiguous())
+                          kh * kw * (alloc0 + alloc1), wp, b.to(device).contiguous(), layout)
     wp = pack_simt(weight.detach(), srcs).to(device)
     return PackedConv(name, cout, kh, kw, stride, pad, alloc0, alloc1, IMPL_SIMT, 0,
                       kh * kw * (alloc0 + alloc1), wp, b.to(device).contiguous())

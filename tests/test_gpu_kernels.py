@@ -57,7 +57,7 @@ CONV_CASES = [
 ]
 
 
-def _run_conv(ops, oracle, case, dtype, prefer_tc):
+def _run_conv(ops, oracle, case, dtype, prefer_tc, tc_layout=None):
     name, H, W, srcs, cout, k, stride, pad, a_pre, a_post, use_gate, use_res, shuffle, out_f32 = case
     cin = sum(r for r, _ in srcs)
     w = rnd((cout, cin, k, k), 1, scale=(1.5 / (cin * k * k) ** 0.5)).to(dtype).float()   # representable in `dtype`
@@ -74,7 +74,8 @@ def _run_conv(ops, oracle, case, dtype, prefer_tc):
     oracle.conv2d(lo, xs[0], xs[1] if len(xs) > 1 else None, exp, gate=gate, res=res, act_pre=a_pre,
                   act_post=a_post, pixel_shuffle=shuffle)
     # cuda
-    lc = packing.pack_conv(name, w, b, srcs, stride, pad, dtype, 'cuda', prefer_tc, 1.0 if a_post == ACT_CLAMP3 else 0.0)
+    lc = packing.pack_conv(name, w, b, srcs, stride, pad, dtype, 'cuda', prefer_tc, 1.0 if a_post == ACT_CLAMP3 else 0.0,
+                           tc_layout=tc_layout)
     out = torch.zeros(oshape, dtype=odt, device='cuda')
     cx = [x.cuda() for x in xs]
     ops.conv2d(lc, cx[0], cx[1] if len(cx) > 1 else None, out, gate=None if gate is None else gate.cuda(),
@@ -93,9 +94,14 @@ def test_conv_simt(cuda_ops, oracle_ops, case, prec):
 
 @pytest.mark.parametrize('case', [c for c in CONV_CASES if c[6] == 1], ids=[c[0] for c in CONV_CASES if c[6] == 1])
 @pytest.mark.parametrize('prec', ['fp16', 'bf16'])
-def test_conv_tc(cuda_ops, oracle_ops, case, prec):
-    lc, out, exp = _run_conv(cuda_ops, oracle_ops, case, DT[prec], prefer_tc=True)
-    assert lc.impl == IMPL_TC, 'stride-1 16-bit convs must take the tcgen05 path'
+@pytest.mark.parametrize('layout', [0, 1])
+def test_conv_tc(cuda_ops, oracle_ops, case, prec, layout):
+    """layout 0: one TMA box per (kx, chunk) stage; layout 1: one box per (tile, chunk), taps as shifted
+    UMMA descriptor views (only where all taps stay resident in shared memory)"""
+    if layout == 1 and packing.choose_layout(case[5], case[5], case[3], packing.choose_nb(case[4])) == 0:
+        pytest.skip('weights of this conv are streamed (layout 0 only)')
+    lc, out, exp = _run_conv(cuda_ops, oracle_ops, case, DT[prec], prefer_tc=True, tc_layout=layout)
+    assert lc.impl == IMPL_TC and lc.layout == layout, 'stride-1 16-bit convs must take the tcgen05 path'
     close(out, exp, TOL[out.dtype] if out.dtype != torch.float32 else 2e-4, f'conv_tc[{case[0]},{prec}]')
 
 

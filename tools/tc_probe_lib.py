@@ -75,46 +75,3 @@ def coords(H, W, a):
     return (y * 0.01 + x * 0.001 + c * 0.1).float()
 
 
-for LAYOUT in (0, 1):
-    print('=== layout', LAYOUT, '===')
-    ok = True
-    ok &= probe('id1x1_c16', 8, 16, [(16, 16)], 16, 1, ident, xfun=coords)
-    ok &= probe('id1x1_c64', 8, 16, [(64, 64)], 64, 1, ident, xfun=coords)
-    ok &= probe('id1x1_c48_big', 20, 40, [(48, 48)], 48, 1, ident, xfun=coords)
-    ok &= probe('rand1x1_c64', 16, 32, [(64, 64)], 32, 1)
-    ok &= probe('id3x3', 16, 32, [(48, 48)], 48, 3, ident, xfun=coords)
-    for dy, dx in ((-1, 0), (1, 0), (0, -1), (0, 1)):
-        ok &= probe(f'shift{dy}{dx}', 16, 32, [(48, 48)], 48, 3, shift(dy, dx), xfun=coords)
-    ok &= probe('rand3x3', 24, 48, [(48, 48)], 48, 3)
-    ok &= probe('rand3x3_2src', 24, 48, [(8, 8), (48, 48)], 48, 3)
-    ok &= probe('rand3x3_n192', 24, 48, [(48, 48)], 192, 3)
-    ok &= probe('rand7x7', 24, 48, [(32, 32)], 64, 7)
-    ok &= probe('rand3x3_bf16', 24, 48, [(48, 48)], 48, 3, dtype=torch.bfloat16)
-    ok &= probe('rand3x3_270x480', 270, 480, [(48, 48)], 48, 3)
-    print('TC_PROBE layout', LAYOUT, 'ALL_OK' if ok else 'FAILED')
-
-
-# matching
-from oracle.oracle_ops import OracleOps
-oo = OracleOps()
-g = torch.Generator().manual_seed(1)
-for split in (False, True):
-    lr_f = torch.rand((32, 48, 16), generator=g) - 0.5
-    ref_f = torch.rand((20, 28, 16), generator=g) - 0.5
-    kpad = 448 if split else 192
-    P, R = 32 * 48, 20 * 28
-    A, B = torch.zeros((P, kpad), dtype=torch.float16), torch.zeros((R, kpad), dtype=torch.float16)
-    oo.patch_pack(lr_f, A, 1 if split else 0)
-    oo.patch_pack(ref_f, B, 2 if split else 0)
-    ce, ie = torch.zeros(P), torch.zeros(P, dtype=torch.int32)
-    oo.match_argmax(A, B, ce, ie)
-    for impl in (0, 1):
-        c = torch.full((P,), float('nan'), device='cuda')
-        i = torch.full((P,), -1, dtype=torch.int32, device='cuda')
-        try:
-            ops.match_argmax(A.cuda(), B.cuda(), c, i, impl=impl)
-            torch.cuda.synchronize()
-            print(f'[match split={split} impl={impl}] conf err {(c.cpu() - ce).abs().max().item():.3e} idx mismatch {(i.cpu() != ie).float().mean().item():.4f}'
-                  f' got {c[:4].tolist()} {i[:4].tolist()} exp {ce[:4].tolist()} {ie[:4].tolist()}')
-        except Exception as e:
-            print(f'[match split={split} impl={impl}] EXCEPTION {e}')
