@@ -131,19 +131,24 @@ def pack_tc(weight, srcs, dtype, nb, layout=0):
 SMEM_BUDGET = 232448 - 1024 - 4096      # opt-in shared memory per CTA minus alignment and static (conv_tc.cu)
 
 
-def choose_layout(kh, kw, srcs, nb):
-    """layout 1 (one TMA box per tile and channel chunk, taps as shifted descriptor views) whenever all taps of
-    all chunks stay resident in shared memory next to >= 3 activation boxes; otherwise layout 0."""
-    import os
-    forced = os.environ.get('REFVSR_TC_LAYOUT')
-    if forced is not None:
-        return int(forced) if (int(forced) == 0 or (kh == kw and kh in (1, 3, 5, 7))) else 0
+def layout1_fits(kh, kw, srcs, nb):
+    """layout 1 needs all taps of all chunks resident in shared memory next to >= 3 activation boxes"""
     if kh != kw or kh not in (1, 3, 5, 7):
-        return 0
+        return False
     nchunks = sum((a + 63) // 64 for _, a in srcs)
     w_all = nchunks * kh * kw * nb * 128
     a_bytes = (16 + kh - 1) * (8 if kw == 1 else 16) * 128
-    return 1 if w_all + 3 * a_bytes <= SMEM_BUDGET else 0
+    return w_all + 3 * a_bytes <= SMEM_BUDGET
+
+
+def choose_layout(kh, kw, srcs, nb):
+    """Default: layout 0 (one TMA box per (kx, chunk) stage).  Layout 1 (one box per tile and chunk, the kh x kw
+    taps as shifted UMMA descriptor views of it) is numerically identical and moves 1.7x fewer bytes from L2, but
+    measured SLOWER end to end on B200 (36.1 vs 30.3 ms / window, profiles/r01_conv_sweep.md), so it is opt-in:
+    REFVSR_TC_LAYOUT=1."""
+    import os
+    forced = int(os.environ.get('REFVSR_TC_LAYOUT', '0'))
+    return 1 if (forced == 1 and layout1_fits(kh, kw, srcs, nb)) else 0
 
 
 def pack_conv(name, weight, bias, srcs, stride, pad, act_dtype, device, prefer_tc=True, bias_add=0.0, tc_layout=None):

@@ -98,7 +98,7 @@ def test_conv_simt(cuda_ops, oracle_ops, case, prec):
 def test_conv_tc(cuda_ops, oracle_ops, case, prec, layout):
     """layout 0: one TMA box per (kx, chunk) stage; layout 1: one box per (tile, chunk), taps as shifted
     UMMA descriptor views (only where all taps stay resident in shared memory)"""
-    if layout == 1 and packing.choose_layout(case[5], case[5], case[3], packing.choose_nb(case[4])) == 0:
+    if layout == 1 and not packing.layout1_fits(case[5], case[5], case[3], packing.choose_nb(case[4])):
         pytest.skip('weights of this conv are streamed (layout 0 only)')
     lc, out, exp = _run_conv(cuda_ops, oracle_ops, case, DT[prec], prefer_tc=True, tc_layout=layout)
     assert lc.impl == IMPL_TC and lc.layout == layout, 'stride-1 16-bit convs must take the tcgen05 path'
