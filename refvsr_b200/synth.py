@@ -35,3 +35,30 @@ def sliding_windows(lrs, refs, t):
     for k in range(n):
         idx = [min(max(k - t // 2 + j, 0), n - 1) for j in range(t)]
         yield k, lrs[idx].unsqueeze(0), refs[idx].unsqueeze(0), (k == 0)
+
+
+def make_clip_range(start, num, h, w, ref_scale=1, seed=1234):
+    """Frames [start, start+num) of an endless synthetic stream: same construction as make_clip but with a
+    bounded, periodic camera path (triangle wave, period 32 frames), so any rank can render exactly the frames it
+    owns (bench.py multi-GPU sharding) from a fixed-size seeded scene."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    H, W = 4 * h, 4 * w
+    amp = 16
+    mx, my = 6 * amp + 8, 3 * amp + 8
+    ch, cw = H + 2 * my, W + 2 * mx
+    scene = 0.0
+    for s_, a_ in ((32, 0.5), (8, 0.3), (2, 0.2)):
+        lo = torch.rand(1, 3, ch // s_ + 3, cw // s_ + 3, generator=g)
+        scene = scene + a_ * F.interpolate(lo, size=(ch, cw), mode='bicubic', align_corners=False)
+    scene = (scene + 0.04 * torch.randn(1, 3, ch, cw, generator=g)).clamp(0, 1)
+    lrs, refs = [], []
+    for k in range(start, start + num):
+        ph = k % (2 * amp)
+        tri = ph if ph <= amp else 2 * amp - ph          # 0..amp..0
+        ox, oy = mx + 6 * tri - 3 * amp, my - 3 * tri + 3 * amp // 2
+        ox, oy = max(0, min(ox, cw - W)), max(0, min(oy, ch - H))
+        hr = scene[:, :, oy:oy + H, ox:ox + W]
+        lrs.append(F.avg_pool2d(hr, 4))
+        crop = hr[:, :, H // 4:H // 4 + H // 2, W // 4:W // 4 + W // 2]
+        refs.append(crop if ref_scale == 2 else F.avg_pool2d(crop, 2))
+    return torch.cat(lrs, 0).contiguous(), torch.cat(refs, 0).contiguous()
