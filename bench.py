@@ -77,12 +77,12 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def make_model(workload, precision, device):
+def make_model(workload, precision, device, graphs=True):
     import torch
     from refvsr_b200 import SRNet, get_config
     from refvsr_b200.modules import seeded_test_weights
     wl = WORKLOADS[workload]
-    cfg = get_config(wl['config'], device=device, b200_precision=precision or wl['precision'])
+    cfg = get_config(wl['config'], device=device, b200_precision=precision or wl['precision'], b200_cuda_graphs=graphs)
     net = SRNet(cfg).eval()
     seeded_test_weights(net, seed=1234)          # random-init weights of the named architecture (no checkpoints offline)
     return cfg, net.to(device)
@@ -215,7 +215,7 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     lib = load_library()
     peaks = measured_peaks()
-    cfg, net = make_model(args.workload, args.precision, dev)
+    cfg, net = make_model(args.workload, args.precision, dev, graphs=not args.no_graphs)
     wl = WORKLOADS[args.workload]
     K, Wm = args.steps, args.warmup
     # One clip of world * n_own frames; rank r owns (decodes) frames [r*n_own, (r+1)*n_own), n_own a multiple of
@@ -291,11 +291,21 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), lib.rv_launch_count() - n0, clocks
 
+    # one-time CUDA-graph capture (one graph per ring phase x window kind, ~16 of them) in an untimed pre-pass over
+    # the same windows, so that the K timed steps measure the steady serving rate rather than capture cost
+    net.Network.reset_state()
+    run_resident(0, Wm + K)
+    n_eager = lib.rv_launch_count()
     ms_res, launches, clocks = timed(run_resident)
     ms_e2e, _, clocks_e2e = timed(run_e2e)
     bad = {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
     if bad & set(clocks['reasons']):                          # re-measure once (timing rules)
-        ms_res, launches, clocks = timed(run_resident)
+        # one-time CUDA-graph capture (one graph per ring phase x window kind, ~16 of them) in an untimed pre-pass over
+    # the same windows, so that the K timed steps measure the steady serving rate rather than capture cost
+    net.Network.reset_state()
+    run_resident(0, Wm + K)
+    n_eager = lib.rv_launch_count()
+    ms_res, launches, clocks = timed(run_resident)
 
     line = None
     if rank == 0:
@@ -317,7 +327,10 @@ def run_ours(args):
             'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': 3 * 16 * H * W * 4, 'ms_per_step': ms_e2e / K,
                     'note': 'pinned host window -> SRNet.forward -> pinned host frame, stream sync every step'},
-            'gpu_launches': int(launches), 'clocks': clocks, 'clocks_e2e': clocks_e2e,
+            'gpu_launches': int(launches) if launches else int(round(n_eager * K / float(Wm + K))),
+            'gpu_launches_note': 'kernels of librefvsr_b200.so executed in the timed region; with CUDA graphs they are '
+                                 'replayed graph nodes, counted from the eager capture pass over the same windows',
+            'clocks': clocks, 'clocks_e2e': clocks_e2e,
             'roofline': dict(roof['conv3x3_lr'], kernel='conv_tc_kernel 3x3 C->C @270x480 (+ReLU+residual)',
                              peak_source=peaks['source'], traffic=None),
             'roofline_other': {k: v for k, v in roof.items() if k != 'conv3x3_lr'},
@@ -396,6 +409,7 @@ def main():
     ap.add_argument('--workload', default='mfid', choices=list(WORKLOADS))
     ap.add_argument('--precision', default=None, choices=[None, 'fp32', 'fp16', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graphs', action='store_true', help='eager kernel launches (for ncu launch lists)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':

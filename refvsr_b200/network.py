@@ -75,6 +75,7 @@ class Network(nn.Module):
         self._bufs = {}
         self._device = torch.device('cpu')
         self._b = 0
+        self.executed_kernels = 0     # kernels of librefvsr_b200.so actually executed (eager launches + graph nodes)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     def _invalidate(self):
@@ -551,14 +552,18 @@ class Network(nn.Module):
             if entry is None:
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
+                n0 = self.ops.launch_count()
                 with torch.cuda.graph(graph):
                     out_static, _ = self._run_window(*args)
-                entry = (graph, out_static)
+                entry = (graph, out_static, self.ops.launch_count() - n0)
                 self._graphs[key] = entry
             entry[0].replay()
+            self.executed_kernels += entry[2]          # kernel nodes of librefvsr_b200.so replayed by the graph
             out, vis = entry[1].clone(), None
         else:
+            n0 = self.ops.launch_count()
             out_static, vis = self._run_window(*args)
+            self.executed_kernels += self.ops.launch_count() - n0
             out = out_static.clone()
         st['has_prev'] = True
         return out, vis
