@@ -24,6 +24,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_REAL_STDOUT = sys.stdout
 
 WORKLOADS = {
     'mfid': dict(config='config_RefVSR_MFID', ref_scale=1, precision='bf16', baseline_cfg=2),
@@ -334,7 +335,7 @@ def run_ours(args):
                 line['cpu_baseline'] = cpu_baseline_sample(args.workload)
             except Exception as ex:  # the checker must never take the bench down
                 line['cpu_baseline'] = {'error': repr(ex)}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -391,10 +392,16 @@ def run_reference(args):
             'config': {'workload': f'{wl["config"]} 4x inference, T={T} (bounded CPU sample, see cpu_baseline.sample)'},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 def main():
+    # libraries (NCCL's version banner, ...) may write to the C-level stdout; the contract is ONE JSON line on stdout,
+    # so fd 1 is pointed at stderr and the JSON goes to a private copy of the original stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=18)
