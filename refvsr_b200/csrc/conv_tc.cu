@@ -156,6 +156,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   const int ntiles = p.tiles_x * p.tiles_y;
   const int nchunks = p.nch0 + p.nch1;
 
+  // Programmatic dependent launch: let the next kernel of the stream start its own prologue as soon as SMs free
+  // up; everything below that reads or writes activations sits behind griddepcontrol.wait, while barrier init,
+  // TMEM allocation, bias and the (constant) weight fetch overlap the previous kernel's tail.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.slots; ++i) {
       tc::mbar_init(&bar_full[i], 1);
@@ -189,6 +194,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         for (int s = 0; s < p.S; ++s)
           tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_w, smemW + (size_t)s * p.w_bytes, p.w_bytes);
       }
+      asm volatile("griddepcontrol.wait;" ::: "memory");   // activations of the previous kernel are now visible
       const uint32_t tx_bytes = p.a_bytes + (p.resident ? 0u : p.w_bytes);
       int slot = 0;
       uint32_t ph = 0;
@@ -279,6 +285,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     const TR* res = reinterpret_cast<const TR*>(p.res);
     TO* out = reinterpret_cast<TO*>(p.out);
     const float pre_slope = p.pre_slope, post_slope = p.post_slope;
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // gate / residual reads and all stores come after this
     constexpr int PRE = 3;  // chunks whose residual / gate vectors are prefetched before the accumulator wait
     const uint32_t acc = (uint32_t)grp;
     uint32_t accph = 0;
@@ -438,7 +445,18 @@ static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& 
     RV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  kern<<<grid, 64 + 128 * NACC, smem, st>>>(tm0, tm1, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(64 + 128 * NACC);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool use_pdl = getenv("REFVSR_NO_PDL") == nullptr;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  RV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm0, tm1, p));
   RV_LAUNCH_CHECK("conv_tc");
   return RV_OK;
 }
