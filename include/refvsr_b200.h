@@ -93,6 +93,29 @@ typedef struct rv_conv_desc {
 
 int rv_conv2d(const rv_conv_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * rv_resblock - fused residual block  out = act_post( x + conv2( act_mid( conv1(x) ) ) ), 3x3 / stride 1 / pad 1,
+ * C -> C -> C channels (C <= 64), f16/bf16 NHWC.  One launch instead of two rv_conv2d calls for
+ * ResidualBlockNoBN (mmedit/models/common/sr_backbone_utils.py:85-97, act_mid = ReLU) and ResBlock
+ * (models/archs/RefVSR_/common.py:33-39, act_mid = LeakyReLU(0.2); act_post = LeakyReLU(0.2) inside
+ * AlignedConv2d, alignment.py:19-21).  w1 / w2: packing.pack_tc(..., layout=1) images ([9 taps][nb][64]).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct rv_resblock_desc {
+  const void* src;   /* [H][W][c] */
+  int32_t c;         /* allocated channels of src (multiple of 8, <= 64) */
+  int32_t dtype;     /* RV_F16 | RV_BF16 (input, intermediate and output) */
+  int32_t H, W;
+  const void* w1;
+  const float* b1;   /* [cout] */
+  const void* w2;
+  const float* b2;
+  int32_t cout, nb, act_mid, act_post;
+  void* out;         /* [H][W][out_cs] */
+  int32_t out_cs;
+} rv_resblock_desc;
+
+int rv_resblock(const rv_resblock_desc* d, void* stream);
+
 /* space-to-depth by 2: out[(Y,X)][(ry*2+rx)*C + c] = src[(2Y+ry, 2X+rx)][c].  Turns the two stride-2
  * convolutions of the path (ref_encoder2.0.0, RefVSR.py:45; aa2.align.p_conv.0, alignment.py:21) into
  * stride-1 3x3 convolutions over 4C channels (weights re-indexed by packing.s2d_weights), so they run on

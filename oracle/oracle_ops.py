@@ -67,6 +67,17 @@ class OracleOps:
         assert out.shape[:2] == o.shape[:2], (layer.name, out.shape, o.shape)
         out[..., :o.shape[2]] = o.to(out.dtype)
 
+    def pack_resblock(self, name, w1, b1, w2, b2, alloc, act_dtype, device):
+        return types.SimpleNamespace(name=name, cout=w1.shape[0], alloc=alloc, w1=w1.detach().float().cpu(), b1=b1.detach().float().cpu(),
+                                     w2=w2.detach().float().cpu(), b2=b2.detach().float().cpu())
+
+    def resblock(self, rb, src, out, act_mid, act_post=0):
+        x = _nchw(src)[:, :rb.cout]
+        t = _act(F.conv2d(x, rb.w1, rb.b1, 1, 1), act_mid)
+        t = t.to(src.dtype).float()                      # the fused kernel stores the intermediate in the activation dtype
+        y = _act(x + F.conv2d(t, rb.w2, rb.b2, 1, 1), act_post)
+        out[..., :rb.cout] = _nhwc(y).to(out.dtype)
+
     def space_to_depth2(self, src, out):
         H, W, C = src.shape
         z = src.view(H // 2, 2, W // 2, 2, C).permute(0, 2, 1, 3, 4).reshape(H // 2, W // 2, 4 * C)

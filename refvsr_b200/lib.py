@@ -35,6 +35,15 @@ class rv_conv_desc(C.Structure):
     ]
 
 
+class rv_resblock_desc(C.Structure):
+    _fields_ = [
+        ('src', C.c_void_p), ('c', C.c_int32), ('dtype', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+        ('w1', C.c_void_p), ('b1', C.c_void_p), ('w2', C.c_void_p), ('b2', C.c_void_p),
+        ('cout', C.c_int32), ('nb', C.c_int32), ('act_mid', C.c_int32), ('act_post', C.c_int32),
+        ('out', C.c_void_p), ('out_cs', C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/refvsr_b200.h one to one (tests check the export list)
 _P, _I, _F = C.c_void_p, C.c_int, C.c_float
 SIGNATURES = {
@@ -42,6 +51,7 @@ SIGNATURES = {
     'rv_version': (_I, []),
     'rv_launch_count': (C.c_uint64, []),
     'rv_conv2d': (_I, [C.POINTER(rv_conv_desc), _P]),
+    'rv_resblock': (_I, [C.POINTER(rv_resblock_desc), _P]),
     'rv_space_to_depth2': (_I, [_P, _I, _I, _I, _I, _P, _P]),
     'rv_prep_image': (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _P]),
     'rv_spynet_resize_norm': (_I, [_P, _I, _I, _P, _I, _I, _P]),
@@ -150,6 +160,18 @@ class CudaOps:
         d.k_real = layer.k_real
         d.layout = getattr(layer, 'layout', 0)
         _check(self.lib, self.lib.rv_conv2d(C.byref(d), self._stream()), f'rv_conv2d[{layer.name}]')
+
+    def resblock(self, rb, src, out, act_mid, act_post=ACT_NONE):
+        """`rb` is a packing.PackedResBlock; out = act_post(src + conv2(act_mid(conv1(src))))"""
+        _chk_dev(src, out)
+        assert src.shape[2] == rb.alloc and src.dtype == out.dtype and src.data_ptr() != out.data_ptr()
+        d = rv_resblock_desc()
+        d.src, d.c, d.dtype = src.data_ptr(), src.shape[2], DTYPE_CODE[src.dtype]
+        d.H, d.W = src.shape[0], src.shape[1]
+        d.w1, d.b1, d.w2, d.b2 = rb.w1.data_ptr(), rb.b1.data_ptr(), rb.w2.data_ptr(), rb.b2.data_ptr()
+        d.cout, d.nb, d.act_mid, d.act_post = rb.cout, rb.nb, act_mid, act_post
+        d.out, d.out_cs = out.data_ptr(), out.shape[2]
+        _check(self.lib, self.lib.rv_resblock(C.byref(d), self._stream()), f'rv_resblock[{rb.name}]')
 
     def space_to_depth2(self, src, out):
         _chk_dev(src, out)

@@ -72,6 +72,7 @@ class Network(nn.Module):
         self.prefer_tc = bool(_cget(config, 'b200_tensor_cores', True))
         self.reuse = bool(_cget(config, 'b200_reuse', True))
         self.use_graphs = bool(_cget(config, 'b200_cuda_graphs', True))
+        self.fuse_resblocks = bool(_cget(config, 'b200_fuse_resblocks', True))
         self._bufs = {}
         self._device = torch.device('cpu')
         self._b = 0
@@ -157,6 +158,25 @@ class Network(nn.Module):
     # ------------------------------------------------------------------------------------------
     # building blocks
     # ------------------------------------------------------------------------------------------
+    def _resblock(self, conv1, conv2, x, out, tmp, act_mid, act_post=ACT_NONE):
+        """out = act_post(x + conv2(act_mid(conv1(x)))): one fused tcgen05 kernel when the block qualifies
+        (16-bit activations, C <= 64), otherwise two convolutions through the scratch buffer `tmp`."""
+        C = x.shape[2]
+        m1, m2 = self.get_submodule(conv1), self.get_submodule(conv2)
+        if (self.fuse_resblocks and self.prefer_tc and hasattr(self.ops, 'resblock')
+                and packing.resblock_fusable(m1.weight, m2.weight, C, self.act_dtype)):
+            key = ('rb', conv1, conv2, C)
+            rb = self._packed.get(key)
+            if rb is None:
+                pack = self.ops.pack_resblock if hasattr(self.ops, 'pack_resblock') else packing.pack_resblock
+                rb = pack(conv1, m1.weight, m1.bias, m2.weight, m2.bias, C, self.act_dtype, self._device)
+                self._packed[key] = rb
+            self.ops.resblock(rb, x, out, act_mid, act_post)
+            return out
+        self._conv(conv1, x, None, tmp, [(C, C)], act_pre=act_mid)
+        self._conv(conv2, tmp, None, out, [(C, C)], res=x, act_post=act_post)
+        return out
+
     def _reslist(self, prefix, n, x, out, tag):
         """ResList (RefVSR_/common.py:64-82): n x [x + conv2(lrelu0.2(conv1(x)))], conv_tail, + input."""
         C = x.shape[2]
@@ -165,9 +185,8 @@ class Network(nn.Module):
         s = [self._buf(tag + '.s0', (H, W, C), x.dtype), self._buf(tag + '.s1', (H, W, C), x.dtype)]
         cur = x
         for i in range(n):
-            self._conv(f'{prefix}.RBs.{i}.conv1', cur, None, t, [(C, C)], act_pre=ACT_LRELU02)
             nxt = s[i % 2]
-            self._conv(f'{prefix}.RBs.{i}.conv2', t, None, nxt, [(C, C)], res=cur)
+            self._resblock(f'{prefix}.RBs.{i}.conv1', f'{prefix}.RBs.{i}.conv2', cur, nxt, t, ACT_LRELU02)
             cur = nxt
         self._conv(f'{prefix}.conv_tail', cur, None, out, [(C, C)], res=x)
         return out
@@ -182,9 +201,8 @@ class Network(nn.Module):
         cur = self._conv(f'{prefix}.main.0', lr8, feat, out if nblk == 0 else s[0], [(3, 8), (C, C)],
                          act_pre=ACT_LRELU01)
         for i in range(nblk):
-            self._conv(f'{prefix}.main.2.{i}.conv1', cur, None, t, [(C, C)], act_pre=ACT_RELU)
             nxt = out if i == nblk - 1 else (s[1] if cur is s[0] else s[0])
-            self._conv(f'{prefix}.main.2.{i}.conv2', t, None, nxt, [(C, C)], res=cur)
+            self._resblock(f'{prefix}.main.2.{i}.conv1', f'{prefix}.main.2.{i}.conv2', cur, nxt, t, ACT_RELU)
             cur = nxt
         return out
 
@@ -284,9 +302,8 @@ class Network(nn.Module):
         dt = self.act_dtype
         a = self._conv('aa2.align.conv1.0', x8, None, self._buf(tag + '.a', (H, W, 32), dt), [(3, 8)],
                        act_pre=ACT_LRELU02, pad=2)
-        t = self._conv('aa2.align.conv1.2.conv1', a, None, self._buf(tag + '.t', (H, W, 32), dt), [(32, 32)],
-                       act_pre=ACT_LRELU02)
-        self._conv('aa2.align.conv1.2.conv2', t, None, out, [(32, 32)], res=a, act_post=ACT_LRELU02)
+        self._resblock('aa2.align.conv1.2.conv1', 'aa2.align.conv1.2.conv2', a, out, self._buf(tag + '.t', (H, W, 32), dt),
+                       ACT_LRELU02, ACT_LRELU02)
         return out
 
     def _aa2(self, lr, ref8, idx, ref_feat, h, w, out):
@@ -305,10 +322,8 @@ class Network(nn.Module):
         ha, wa = (H2 + 4 - 5) // ks + 1, (W2 + 4 - 5) // ks + 1
         p0 = self._conv('aa2.align.p_conv.0', rf, qf, self._buf('aa2.p0', (ha, wa, 32), dt), [(32, 32), (32, 32)],
                         act_pre=ACT_LRELU02, stride=ks, pad=2)
-        pt = self._conv('aa2.align.p_conv.2.conv1', p0, None, self._buf('aa2.pt', (ha, wa, 32), dt), [(32, 32)],
-                        act_pre=ACT_LRELU02)
-        p1 = self._conv('aa2.align.p_conv.2.conv2', pt, None, self._buf('aa2.p1', (ha, wa, 32), dt), [(32, 32)],
-                        res=p0, act_post=ACT_LRELU02)
+        p1 = self._resblock('aa2.align.p_conv.2.conv1', 'aa2.align.p_conv.2.conv2', p0, self._buf('aa2.p1', (ha, wa, 32), dt),
+                            self._buf('aa2.pt', (ha, wa, 32), dt), ACT_LRELU02, ACT_LRELU02)
         affine = self._buf('aa2.aff', (ha, wa, 3), torch.float32)
         self._conv('aa2.align.p_conv.4', p1, None, affine, [(32, 32)], act_post=ACT_CLAMP3, pad=0, bias_add=1.0)
         self.ops.aligned_sample(warped, affine, ks, out)

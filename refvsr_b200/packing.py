@@ -168,3 +168,31 @@ def pack_conv(name, weight, bias, srcs, stride, pad, act_dtype, device, prefer_t
     wp = pack_simt(weight.detach(), srcs).to(device)
     return PackedConv(name, cout, kh, kw, stride, pad, alloc0, alloc1, IMPL_SIMT, 0,
                       kh * kw * (alloc0 + alloc1), wp, b.to(device).contiguous())
+
+
+@dataclass
+class PackedResBlock:
+    name: str
+    cout: int
+    alloc: int
+    nb: int
+    w1: torch.Tensor
+    b1: torch.Tensor
+    w2: torch.Tensor
+    b2: torch.Tensor
+
+
+def resblock_fusable(w1, w2, alloc, act_dtype):
+    c = w1.shape[0]
+    return (act_dtype in (torch.float16, torch.bfloat16) and tuple(w1.shape) == (c, c, 3, 3) and tuple(w2.shape) == (c, c, 3, 3)
+            and alloc % 8 == 0 and c <= alloc <= 64)
+
+
+def pack_resblock(name, w1, b1, w2, b2, alloc, act_dtype, device):
+    """both 3x3 convs of a residual block in the single-box layout ([1][1][9 taps][nb][64]) for rv_resblock"""
+    c = w1.shape[0]
+    nb = (c + 15) // 16 * 16
+    p1 = pack_tc(w1.detach(), [(c, alloc)], act_dtype, nb, layout=1).to(device)
+    p2 = pack_tc(w2.detach(), [(c, alloc)], act_dtype, nb, layout=1).to(device)
+    return PackedResBlock(name, c, alloc, nb, p1, b1.detach().float().to(device).contiguous(), p2,
+                          b2.detach().float().to(device).contiguous())

@@ -105,6 +105,58 @@ def test_conv_tc(cuda_ops, oracle_ops, case, prec, layout):
     close(out, exp, TOL[out.dtype] if out.dtype != torch.float32 else 2e-4, f'conv_tc[{case[0]},{prec}]')
 
 
+RB_CASES = [  # name, H, W, C(real), alloc, act_mid, act_post
+    ('noBN48', 37, 53, 48, 48, ACT_RELU, ACT_NONE),
+    ('res48', 64, 40, 48, 48, ACT_LRELU02, ACT_NONE),
+    ('align32', 30, 44, 32, 32, ACT_LRELU02, ACT_LRELU02),
+    ('small24', 33, 21, 24, 24, ACT_RELU, ACT_NONE),
+    ('tiny', 3, 5, 48, 48, ACT_RELU, ACT_NONE),
+    ('one_tile_exact', 16, 8, 48, 48, ACT_RELU, ACT_NONE),
+]
+
+
+@pytest.mark.parametrize('case', RB_CASES, ids=[c[0] for c in RB_CASES])
+@pytest.mark.parametrize('prec', ['fp16', 'bf16'])
+def test_resblock_fused(cuda_ops, oracle_ops, case, prec):
+    """rv_resblock (one launch: conv -> act -> conv -> +x) against the oracle's two convolutions"""
+    name, H, W, C, alloc, a_mid, a_post = case
+    dt = DT[prec]
+    w1 = rnd((C, C, 3, 3), 1, scale=1.5 / (C * 9) ** 0.5).to(dt).float()
+    w2 = rnd((C, C, 3, 3), 2, scale=1.5 / (C * 9) ** 0.5).to(dt).float()
+    b1, b2 = rnd((C,), 3, scale=0.2), rnd((C,), 4, scale=0.2)
+    x = rnd((H, W, alloc), 5, dt)
+    ro = oracle_ops.pack_resblock(name, w1, b1, w2, b2, alloc, dt, 'cpu')
+    exp = torch.zeros((H, W, C))
+    oracle_ops.resblock(ro, x, exp, a_mid, a_post)
+    rc = packing.pack_resblock(name, w1, b1, w2, b2, alloc, dt, 'cuda')
+    out = torch.zeros((H, W, alloc), dtype=dt, device='cuda')
+    cuda_ops.resblock(rc, x.cuda(), out, a_mid, a_post)
+    torch.cuda.synchronize()
+    close(out[..., :C], exp, TOL[dt], f'resblock[{name},{prec}]')
+
+
+def test_resblock_fused_full_size_matches_two_convs(cuda_ops):
+    """270x480x48: fused kernel == conv_tc + conv_tc (same 16-bit intermediate rounding)"""
+    H, W, C = 270, 480, 48
+    dt = torch.bfloat16
+    w1 = rnd((C, C, 3, 3), 1, scale=0.07).to(dt).float()
+    w2 = rnd((C, C, 3, 3), 2, scale=0.07).to(dt).float()
+    b1, b2 = rnd((C,), 3, scale=0.1), rnd((C,), 4, scale=0.1)
+    x = rnd((H, W, C), 5, dt).cuda()
+    l1 = packing.pack_conv('a', w1, b1, [(C, C)], 1, 1, dt, 'cuda', True)
+    l2 = packing.pack_conv('b', w2, b2, [(C, C)], 1, 1, dt, 'cuda', True)
+    t = torch.zeros((H, W, C), dtype=dt, device='cuda')
+    ref = torch.zeros((H, W, C), dtype=dt, device='cuda')
+    cuda_ops.conv2d(l1, x, None, t, act_pre=ACT_RELU)
+    cuda_ops.conv2d(l2, t, None, ref, res=x)
+    rb = packing.pack_resblock('rb', w1, b1, w2, b2, C, dt, 'cuda')
+    out = torch.zeros((H, W, C), dtype=dt, device='cuda')
+    cuda_ops.resblock(rb, x, out, ACT_RELU)
+    torch.cuda.synchronize()
+    close(out, ref, 1e-2, 'fused vs two convs')
+    assert (out.float() - ref.float()).abs().mean().item() < 2e-3
+
+
 def test_conv_tc_large_matches_simt(cuda_ops):
     """full-size property: tcgen05 path == CUDA-core path on a 270x480x48 map (fp16 storage ulp)."""
     H, W, C = 270, 480, 48
