@@ -78,12 +78,13 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def make_model(workload, precision, device, graphs=True):
+def make_model(workload, precision, device, graphs=True, fuse=False):
     import torch
     from refvsr_b200 import SRNet, get_config
     from refvsr_b200.modules import seeded_test_weights
     wl = WORKLOADS[workload]
-    cfg = get_config(wl['config'], device=device, b200_precision=precision or wl['precision'], b200_cuda_graphs=graphs)
+    cfg = get_config(wl['config'], device=device, b200_precision=precision or wl['precision'], b200_cuda_graphs=graphs,
+                     b200_fuse_resblocks=fuse)
     net = SRNet(cfg).eval()
     seeded_test_weights(net, seed=1234)          # random-init weights of the named architecture (no checkpoints offline)
     return cfg, net.to(device)
@@ -146,6 +147,13 @@ def kernel_rooflines(net, peaks):
     out['conv3x3_lr'] = dict(bound='tensor', achieved=flops / tconv / 1e12, peak=peaks['tensor_burst'], unit='TFLOP/s',
                              frac=flops / tconv / 1e12 / peaks['tensor_burst'], seconds=tconv,
                              algorithmic_flops=flops, bytes_min=3.0 * C * H * W * e)
+    # fused residual block (rv_resblock): conv3x3 -> ReLU -> conv3x3 -> + x in one launch
+    if net.Network.fuse_resblocks and dt != torch.float32:
+        rb = packing.pack_resblock('bench.rbf', w, torch.zeros(C), w, torch.zeros(C), C, dt, dev)
+        trb = timeit(lambda i: ops.resblock(rb, xs[i % nrot], ys[i % nrot], ACT_RELU))
+        out['resblock_lr'] = dict(bound='tensor', achieved=2 * flops / trb / 1e12, peak=peaks['tensor_burst'], unit='TFLOP/s',
+                                  frac=2 * flops / trb / 1e12 / peaks['tensor_burst'], seconds=trb,
+                                  algorithmic_flops=2 * flops, bytes_min=2.0 * C * H * W * e)
     # K1: flow warp of the (C, 2h, 2w) feature with the on-the-fly x2 flow upsample (largest of the 3 warps)
     flow = torch.randn((H, W, 2), device=dev)
     nrot2 = max(2, int(160e6 // (4 * H * W * C * e)) + 1)
@@ -216,7 +224,7 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     lib = load_library()
     peaks = measured_peaks()
-    cfg, net = make_model(args.workload, args.precision, dev, graphs=not args.no_graphs)
+    cfg, net = make_model(args.workload, args.precision, dev, graphs=not args.no_graphs, fuse=args.fuse)
     wl = WORKLOADS[args.workload]
     K, Wm = args.steps, args.warmup
     # One clip of world * n_own frames; rank r owns (decodes) frames [r*n_own, (r+1)*n_own), n_own a multiple of
@@ -411,6 +419,7 @@ def main():
     ap.add_argument('--precision', default=None, choices=[None, 'fp32', 'fp16', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graphs', action='store_true', help='eager kernel launches (for ncu launch lists)')
+    ap.add_argument('--fuse', action='store_true', help='use the fused residual-block kernel (rv_resblock)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':

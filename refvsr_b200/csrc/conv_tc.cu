@@ -50,6 +50,13 @@ struct TcP {
   //                mode 1 = 16 rows x 8 cols, ONE box per (chunk) stage with x- and y-halo, taps = shifted views
   int single_box, th, tw, tw_shift, bw;   // bw = box width in pixels (mode 1: 8 or 16)
   int bo_force;                           // experiment hook: constant base_offset for kx != 0 taps (-1 = kx)
+  // layout 2: operands staged with SWIZZLE_32B in 16-channel quads (32-byte rows): one UMMA_K = 16 slice is a
+  // whole row, so each tcgen05.mma fetches exactly its operand bytes (with 128-byte rows every K-slice pulls the
+  // full row: ~110 cycles per MMA at N = 48, measured - profiles/r01_conv_knockout.md)
+  int sw32, nq0, nq1;
+  uint32_t q_bytes;                       // bytes of one quad sub-buffer of an A stage
+  int dbg;                                // experiment hook (REFVSR_CONV_DBG): 1 no MMA, 2 no epilogue global traffic,
+                                          // 4 no TMEM loads, 8 no TMA box loads
 };
 
 template <typename T>
@@ -96,14 +103,15 @@ __device__ __forceinline__ void store16(T* p, const float v[16]) {
 // start addresses advance by +2 (32 bytes) per K-slice and by one tile row block per tap.
 template <int KH>
 __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t idesc, int ksteps,
-                                           uint32_t b_tap, uint32_t& accumulate) {
+                                           uint32_t b_tap, uint32_t& accumulate, uint32_t alt = 0) {
 #pragma unroll
   for (int ky = 0; ky < KH; ++ky) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (k < ksteps) {
-        tc::umma_f16(d_tmem, ad + (uint64_t)(ky * (TW * 128 / 16) + k * 2), bd + (uint64_t)(ky * b_tap + k * 2), idesc,
-                     accumulate);
+        // alt != 0 (timing experiment only): consecutive MMAs hit different accumulators -> no RAW chain on D
+        tc::umma_f16(d_tmem + (((ky * 4 + k) % 3) * alt), ad + (uint64_t)(ky * (TW * 128 / 16) + k * 2),
+                     bd + (uint64_t)(ky * b_tap + k * 2), idesc, accumulate);
         accumulate = 1;
       }
     }
@@ -205,8 +213,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         int kx = 0, ch = 0;
         for (int s = 0; s < p.S; ++s) {
           tc::mbar_wait(&bar_empty[slot], ph ^ 1u);
+          if (p.dbg & 8) {
+            tc::mbar_arrive(&bar_full[slot]);
+            if (++ch == nchunks) { ch = 0; kx += p.single_box ? 0 : 1; }
+            if (++slot == p.slots) { slot = 0; ph ^= 1u; }
+            continue;
+          }
           tc::mbar_expect_tx(&bar_full[slot], tx_bytes);
           uint8_t* dstA = smemA + (size_t)slot * p.a_bytes;
+          if (p.sw32) {
+            // stage = kx; one 16-channel box per quad of src0 | src1
+            for (int qd = 0; qd < p.nq0 + p.nq1; ++qd) {
+              if (qd < p.nq0)
+                tc::tma_load_3d(&tm0, &bar_full[slot], dstA + (size_t)qd * p.q_bytes, qd * 16, xc + kx, yc);
+              else
+                tc::tma_load_3d(&tm1, &bar_full[slot], dstA + (size_t)qd * p.q_bytes, (qd - p.nq0) * 16, xc + kx, yc);
+            }
+            if (!p.resident)
+              tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_full[slot], smemW + (size_t)slot * p.w_bytes, p.w_bytes);
+            ++kx;
+            if (++slot == p.slots) { slot = 0; ph ^= 1u; }
+            continue;
+          }
           if (ch < p.nch0)
             tc::tma_load_3d(&tm0, &bar_full[slot], dstA, ch * 64, xc + kx, yc);
           else
@@ -230,6 +258,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(smemA)) +
                               (p.single_box ? ((uint64_t)((p.bw * 128 - 1024) >> 4) << 32) : 0ull);
       const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(smemW));
+      const uint64_t adesc32 = tc::umma_desc_sw32(tc::smem_u32(smemA)), bdesc32 = tc::umma_desc_sw32(tc::smem_u32(smemW));
       const uint32_t a_step = p.a_bytes >> 4, w_step = p.w_bytes >> 4, b_tap = (uint32_t)(p.NB * 128) >> 4;
       if (p.resident) tc::mbar_wait(&bar_w, 0);
       int slot = 0;
@@ -247,7 +276,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)(p.resident ? s : slot) * w_step);
           tc::mbar_wait(&bar_full[slot], ph);
           tc::tc_fence_after();
-          if (p.single_box) {
+          if (p.dbg & 1) {
+          } else if (p.sw32) {
+            const uint64_t ad32 = adesc32 + (uint64_t)((uint32_t)slot * a_step);
+            const uint64_t bd32 = bdesc32 + (uint64_t)((uint32_t)(p.resident ? s : slot) * w_step);
+            const int nq = p.nq0 + p.nq1;
+            const uint32_t q_step = p.q_bytes >> 4, bq = (uint32_t)(p.NB * 32) >> 4;
+            for (int ky = 0; ky < p.kh; ++ky)
+              for (int qd = 0; qd < nq; ++qd) {
+                tc::umma_f16(d_tmem, ad32 + (uint64_t)(qd * q_step + ky * (TW * 32 / 16)), bd32 + (uint64_t)((ky * nq + qd) * bq),
+                             idesc, accumulate);
+                accumulate = 1;
+              }
+          } else if (p.single_box) {
             switch (p.kh) {
               case 1: issue_taps_box<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
               case 3: issue_taps_box<3>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
@@ -257,7 +298,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           } else
           switch (p.kh) {
             case 1: issue_taps<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
-            case 3: issue_taps<3>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
+            case 3: issue_taps<3>((p.dbg & 16) ? tmem_base : d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate, (p.dbg & 16) ? p.acc_stride : 0); break;
             case 5: issue_taps<5>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
             case 7: issue_taps<7>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
             default:
@@ -300,7 +341,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
 #pragma unroll
       for (int c = 0; c < PRE; ++c) {
         const int n0 = nblk * p.NB + c * 16;
-        pre_ok[c] = valid && (c * 16 < p.NB) && (n0 + 16 <= p.cout) && p.vec_ok;
+        pre_ok[c] = valid && (c * 16 < p.NB) && (n0 + 16 <= p.cout) && p.vec_ok && !(p.dbg & 2);
         if (pre_ok[c] && res != nullptr && sizeof(TR) == 2) {
           const uint4* q4 = reinterpret_cast<const uint4*>(res + pix * p.res_cs + n0);
           rp[c][0] = __ldg(q4);
@@ -320,10 +361,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         const int c0 = c * 16;
         if (c0 >= p.NB) break;
         const int n0 = nblk * p.NB + c0;
-        const bool live = valid && n0 < p.cout;
+        const bool live = valid && n0 < p.cout && !(p.dbg & 2);
         const bool full = (n0 + 16 <= p.cout);
         const bool vec = full && p.vec_ok;
         const bool pre = (c < PRE) && pre_ok[c < PRE ? c : 0];
+        if (p.dbg & 4) continue;
         float g[16], rr[16];
         if (live && gate) {
           if (pre) {
@@ -418,16 +460,16 @@ PFN_tmapEncodeTiled get_tmap_encoder() {
   return fn;
 }
 
-static int make_act_tmap(CUtensorMap* m, const void* ptr, int C, int W, int H, int box_w, int box_rows, int fmt) {
+static int make_act_tmap(CUtensorMap* m, const void* ptr, int C, int W, int H, int box_w, int box_rows, int fmt, int sw32 = 0) {
   PFN_tmapEncodeTiled enc = get_tmap_encoder();
   if (!enc) return fail(RV_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H};
   cuuint64_t gstr[2] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_w, (cuuint32_t)box_rows};
+  cuuint32_t box[3] = {sw32 ? 16u : 64u, (cuuint32_t)box_w, (cuuint32_t)box_rows};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
                    const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   sw32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(RV_E_CUDA, "cuTensorMapEncodeTiled failed (%d) C=%d W=%d H=%d", (int)r, C, W, H);
   return RV_OK;
@@ -487,7 +529,7 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   const int nblk = (d->cout + p.NB - 1) / p.NB;
   const size_t budget = (size_t)g_max_smem - 1024 /*alignment*/ - 4096 /*static: barriers, bias*/;
   // mode 1 (single box per tile and chunk) when the whole weight set stays resident next to >= 2 boxes
-  p.single_box = 0;
+  p.single_box = 0; p.sw32 = 0; p.nq0 = p.nq1 = 0; p.q_bytes = 0;
   if (d->layout == 1) {
     RV_REQUIRE(d->kh == d->kw && (d->kh == 1 || d->kh == 3 || d->kh == 5 || d->kh == 7), "rv_conv2d(tc): layout 1 needs a square 1/3/5/7 kernel");
     p.single_box = 1;
@@ -499,6 +541,14 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
     p.a_bytes = (uint32_t)(p.th + d->kh - 1) * p.bw * 128;
     p.w_bytes = (uint32_t)d->kh * d->kw * p.NB * 128;
     RV_REQUIRE((size_t)p.S * p.w_bytes + 2 * (size_t)p.a_bytes <= budget, "rv_conv2d(tc): layout 1 weights do not fit in shared memory");
+  } else if (d->layout == 2) {
+    p.sw32 = 1;
+    p.th = TH; p.tw = TW; p.tw_shift = 4; p.bw = TW;
+    p.nq0 = (p.c0 + 15) / 16; p.nq1 = (p.c1 + 15) / 16;
+    p.S = d->kw;
+    p.q_bytes = (uint32_t)(TH + d->kh - 1) * TW * 32;
+    p.a_bytes = (uint32_t)(p.nq0 + p.nq1) * p.q_bytes;
+    p.w_bytes = (uint32_t)d->kh * (p.nq0 + p.nq1) * p.NB * 32;
   } else {
     p.th = TH; p.tw = TW; p.tw_shift = 4; p.bw = TW;
     p.S = d->kw * (p.nch0 + p.nch1);
@@ -506,6 +556,7 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
     p.w_bytes = (uint32_t)d->kh * p.NB * 128;
   }
   { const char* e = getenv("REFVSR_BO_FORCE"); p.bo_force = e ? atoi(e) : -1; }
+  { const char* e = getenv("REFVSR_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.tiles_x = (p.Wo + p.tw - 1) / p.tw; p.tiles_y = (p.Ho + p.th - 1) / p.th;
   // shared-memory plan: weights resident when they leave room for >= 3 A slots
   const size_t w_all = (size_t)p.S * p.w_bytes;
@@ -537,10 +588,10 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   p.tmem_cols = cols;
 
   CUtensorMap tm0, tm1;
-  int rc = make_act_tmap(&tm0, d->src0, p.c0, d->W, d->H, p.bw, p.th + d->kh - 1, p.fmt);
+  int rc = make_act_tmap(&tm0, d->src0, p.c0, d->W, d->H, p.bw, p.th + d->kh - 1, p.fmt, p.sw32);
   if (rc) return rc;
   if (p.nch1) {
-    rc = make_act_tmap(&tm1, d->src1, p.c1, d->W, d->H, p.bw, p.th + d->kh - 1, p.fmt);
+    rc = make_act_tmap(&tm1, d->src1, p.c1, d->W, d->H, p.bw, p.th + d->kh - 1, p.fmt, p.sw32);
     if (rc) return rc;
   } else {
     tm1 = tm0;

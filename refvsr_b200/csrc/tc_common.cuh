@@ -151,6 +151,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                    // SWIZZLE_128B       bits [61,64)
   return d;
 }
+// K-major operand tile with SWIZZLE_32B: rows of 32 bytes (16 x 16-bit = one UMMA_K slice), 8-row groups 256 bytes
+// apart; 16-byte chunk j of row r sits at chunk j ^ ((r >> 2) & 1)  (Swizzle<1,4,3>: address bit 4 ^= bit 7).
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                    // LBO (unused)
+  d |= (uint64_t)(256 >> 4) << 32;           // SBO = 256 B
+  d |= (uint64_t)1 << 46;                    // descriptor version
+  d |= (uint64_t)6 << 61;                    // SWIZZLE_32B
+  return d;
+}
 // kind::f16 instruction descriptor: fp32 accumulate, A/B both `fmt` (0 = f16, 1 = bf16), K-major
 __host__ __device__ __forceinline__ uint32_t umma_idesc(int fmt, int M, int N) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |

@@ -72,7 +72,9 @@ class Network(nn.Module):
         self.prefer_tc = bool(_cget(config, 'b200_tensor_cores', True))
         self.reuse = bool(_cget(config, 'b200_reuse', True))
         self.use_graphs = bool(_cget(config, 'b200_cuda_graphs', True))
-        self.fuse_resblocks = bool(_cget(config, 'b200_fuse_resblocks', True))
+        # fused residual-block kernel: validated, but not faster than two conv launches yet (MMA-instruction bound,
+        # profiles/r01_conv_knockout.md) -> opt-in
+        self.fuse_resblocks = bool(_cget(config, 'b200_fuse_resblocks', False))
         self._bufs = {}
         self._device = torch.device('cpu')
         self._b = 0

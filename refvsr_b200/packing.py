@@ -92,6 +92,36 @@ def choose_nb(cout):
     return 64
 
 
+def pack_tc_sw32(weight, srcs, dtype, nb):
+    """layout 2: [nblk][kx][ky][quad][NB][16], every [NB][16] slab = byte image of a K-major SWIZZLE_32B operand
+    (32-byte rows; 16-byte chunk j of row r at j ^ ((r >> 2) & 1)).  Quads = 16-channel groups of src0 then src1."""
+    cout, _, kh, kw = weight.shape
+    w = weight.float()
+    nblk = (cout + nb - 1) // nb
+    quads, o = [], 0
+    for real, alloc in srcs:
+        ws = w[:, o:o + real]
+        o += real
+        for j in range((alloc + 15) // 16):
+            sl = ws[:, 16 * j: min(16 * j + 16, real)] if 16 * j < real else ws[:, :0]
+            if sl.shape[1] < 16:
+                sl = torch.cat([sl, w.new_zeros(cout, 16 - sl.shape[1], kh, kw)], 1)
+            quads.append(sl)
+    nq = len(quads)
+    wq = torch.stack(quads, 0)                                  # (nq, cout, 16, kh, kw)
+    wpad = w.new_zeros(nq, nblk * nb, 16, kh, kw)
+    wpad[:, :cout] = wq
+    t = wpad.view(nq, nblk, nb, 16, kh, kw).permute(1, 5, 4, 0, 2, 3).contiguous()   # (nblk, kx, ky, q, n, c)
+    t = t.view(nblk, kw, kh, nq, nb, 2, 8)
+    out = torch.empty_like(t)
+    for m in range(2):                                          # rows with ((r >> 2) & 1) == m swap their two chunks iff m
+        rows = [r for r in range(nb) if ((r >> 2) & 1) == m]
+        idx = torch.tensor(rows, device=t.device)
+        src = t.index_select(4, idx)
+        out.index_copy_(4, idx, src.flip(5) if m else src)
+    return out.view(nblk, kw, kh, nq, nb, 16).to(dtype).contiguous()
+
+
 def pack_tc(weight, srcs, dtype, nb, layout=0):
     cout, _, kh, kw = weight.shape
     w = weight.float()
@@ -128,6 +158,7 @@ def pack_tc(weight, srcs, dtype, nb, layout=0):
     return out.view(nblk, S, kh_eff, nb, 64).to(dtype).contiguous()
 
 
+DEFAULT_TC_LAYOUT = 0                    # 0: 128B-swizzled 64-channel boxes, 2: 32B-swizzled 16-channel quads
 SMEM_BUDGET = 232448 - 1024 - 4096      # opt-in shared memory per CTA minus alignment and static (conv_tc.cu)
 
 
@@ -147,8 +178,10 @@ def choose_layout(kh, kw, srcs, nb):
     measured SLOWER end to end on B200 (36.1 vs 30.3 ms / window, profiles/r01_conv_sweep.md), so it is opt-in:
     REFVSR_TC_LAYOUT=1."""
     import os
-    forced = int(os.environ.get('REFVSR_TC_LAYOUT', '0'))
-    return 1 if (forced == 1 and layout1_fits(kh, kw, srcs, nb)) else 0
+    forced = int(os.environ.get('REFVSR_TC_LAYOUT', str(DEFAULT_TC_LAYOUT)))
+    if forced == 1:
+        return 1 if layout1_fits(kh, kw, srcs, nb) else 0
+    return forced
 
 
 def pack_conv(name, weight, bias, srcs, stride, pad, act_dtype, device, prefer_tc=True, bias_add=0.0, tc_layout=None):
@@ -162,7 +195,8 @@ def pack_conv(name, weight, bias, srcs, stride, pad, act_dtype, device, prefer_t
     if tc_ok:
         nb = choose_nb(cout)
         layout = choose_layout(kh, kw, srcs, nb) if tc_layout is None else tc_layout
-        wp = pack_tc(weight.detach(), srcs, act_dtype, nb, layout).to(device)
+        wp = (pack_tc_sw32(weight.detach(), srcs, act_dtype, nb) if layout == 2
+              else pack_tc(weight.detach(), srcs, act_dtype, nb, layout)).to(device)
         return PackedConv(name, cout, kh, kw, stride, pad, alloc0, alloc1, IMPL_TC, nb,
                           kh * kw * (alloc0 + alloc1), wp, b.to(device).contiguous(), layout)
     wp = pack_simt(weight.detach(), srcs).to(device)

@@ -75,7 +75,7 @@ def coords(H, W, a):
     return (y * 0.01 + x * 0.001 + c * 0.1).float()
 
 
-for LAYOUT in (0, 1):
+for LAYOUT in (0, 1, 2):
     print('=== layout', LAYOUT, '===')
     ok = True
     ok &= probe('id1x1_c16', 8, 16, [(16, 16)], 16, 1, ident, xfun=coords)
