@@ -292,14 +292,14 @@ __global__ void warp_kernel(const T* __restrict__ src, int Hi, int Wi, int C,
 // offsets (clamped) and weights (zeroed when the corner is outside the image) into shared memory;
 // phase 2 is a branch-free 4-tap gather with one thread per (pixel, 16-byte channel vector), so global
 // loads and stores stay fully coalesced along the NHWC channel axis.
-template <typename T, int V>
+template <typename T, int V, int NV>
 __global__ void __launch_bounds__(256) warp_vec_kernel(const T* __restrict__ src, int Hi, int Wi, int C,
                                                        const float* __restrict__ flow, int hf, int wf,
                                                        int flow_up2, T* __restrict__ out, int ppb) {
   __shared__ float4 s_w[256];
   __shared__ int4 s_o[256];
   const int Ho = flow_up2 ? 2 * hf : hf, Wo = flow_up2 ? 2 * wf : wf;
-  const int cv = C / V;
+  const int cv = C / (V * NV);      // threads per pixel; each moves NV consecutive 16-byte vectors
   const int npix = Ho * Wo;
   const int p0 = blockIdx.x * ppb;
   if (threadIdx.x < ppb && p0 + threadIdx.x < npix) {
@@ -348,14 +348,23 @@ __global__ void __launch_bounds__(256) warp_vec_kernel(const T* __restrict__ src
   if (pl >= ppb || p0 + pl >= npix) return;
   const float4 wq = s_w[pl];
   const int4 o = s_o[pl];
-  const T* base = src + (size_t)vc * V;
-  Vec<T, V> t0 = ldv<T, V>(base + (size_t)o.x * C), t1 = ldv<T, V>(base + (size_t)o.y * C),
-            t2 = ldv<T, V>(base + (size_t)o.z * C), t3 = ldv<T, V>(base + (size_t)o.w * C);
-  Vec<T, V> r;
+  const T* base = src + (size_t)vc * (V * NV);
+  Vec<T, V> t0[NV], t1[NV], t2[NV], t3[NV];
 #pragma unroll
-  for (int k = 0; k < V; ++k)
-    r.v[k] = from_f<T>(to_f(t0.v[k]) * wq.x + to_f(t1.v[k]) * wq.y + to_f(t2.v[k]) * wq.z + to_f(t3.v[k]) * wq.w);
-  stv<T, V>(out + (size_t)(p0 + pl) * C + (size_t)vc * V, r);
+  for (int n = 0; n < NV; ++n) {          // all 4*NV loads in flight before any use
+    t0[n] = ldv<T, V>(base + (size_t)o.x * C + n * V);
+    t1[n] = ldv<T, V>(base + (size_t)o.y * C + n * V);
+    t2[n] = ldv<T, V>(base + (size_t)o.z * C + n * V);
+    t3[n] = ldv<T, V>(base + (size_t)o.w * C + n * V);
+  }
+#pragma unroll
+  for (int n = 0; n < NV; ++n) {
+    Vec<T, V> r;
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+      r.v[k] = from_f<T>(to_f(t0[n].v[k]) * wq.x + to_f(t1[n].v[k]) * wq.y + to_f(t2[n].v[k]) * wq.z + to_f(t3[n].v[k]) * wq.w);
+    stv<T, V>(out + (size_t)(p0 + pl) * C + (size_t)vc * (V * NV) + n * V, r);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -634,9 +643,12 @@ static int warp_launch(const void* src, int Hi, int Wi, int C, const float* flow
   constexpr int VMAX = 16 / sizeof(T);
   long long px = (long long)(up2 ? 4 : 1) * hf * wf;
   bool aligned = ((uintptr_t)src % 16 == 0) && ((uintptr_t)out % 16 == 0);
-  if (C % VMAX == 0 && aligned && C / VMAX <= 256) {
-    const int cv = C / VMAX, ppb = 256 / cv;   // pixels per block
-    warp_vec_kernel<T, VMAX><<<cdiv(px, ppb), 256, 0, st>>>((const T*)src, Hi, Wi, C, flow, hf, wf, up2, (T*)out, ppb);
+  if (C % (2 * VMAX) == 0 && aligned && C / (2 * VMAX) <= 256) {
+    const int cv = C / (2 * VMAX), ppb = 256 / cv;   // pixels per block, 32 bytes per thread
+    warp_vec_kernel<T, VMAX, 2><<<cdiv(px, ppb), 256, 0, st>>>((const T*)src, Hi, Wi, C, flow, hf, wf, up2, (T*)out, ppb);
+  } else if (C % VMAX == 0 && aligned && C / VMAX <= 256) {
+    const int cv = C / VMAX, ppb = 256 / cv;
+    warp_vec_kernel<T, VMAX, 1><<<cdiv(px, ppb), 256, 0, st>>>((const T*)src, Hi, Wi, C, flow, hf, wf, up2, (T*)out, ppb);
   } else {
     long long n = px * C;
     warp_kernel<T, 1><<<cdiv(n, 256), 256, 0, st>>>((const T*)src, Hi, Wi, C, flow, hf, wf, up2, (T*)out);

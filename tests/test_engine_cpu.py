@@ -31,6 +31,32 @@ def test_schedule_matches_reference_golden(name, oracle_ops):
             assert mism <= 1e-3
 
 
+def test_fused_resblock_schedule_matches_reference_golden(oracle_ops):
+    """the opt-in fused residual-block route (ops.resblock) computes the same network"""
+    from refvsr_b200.synth import sliding_windows
+    spec, cfg, net, lrs, refs, golden = build_case('small_t7_24x32', 'cpu', ops=oracle_ops, b200_precision='fp32',
+                                                   b200_fuse_resblocks=True)
+    net.Network.act_dtype = torch.float32
+    calls = {'n': 0}
+    orig = oracle_ops.resblock
+
+    def counting(*a, **k):
+        calls['n'] += 1
+        return orig(*a, **k)
+    oracle_ops.resblock = counting
+    try:
+        import refvsr_b200.packing as packing
+        old = packing.resblock_fusable
+        packing.resblock_fusable = lambda w1, w2, alloc, dt: tuple(w1.shape) == tuple(w2.shape) and w1.shape[2] == 3 and alloc <= 64
+        for k, wl, wr, first in sliding_windows(lrs, refs, spec['T']):
+            o = net(wl, wr, first)['result']
+            assert psnr(o[0], torch.from_numpy(golden[f'result_{k}'])) > 95.0
+    finally:
+        oracle_ops.resblock = orig
+        packing.resblock_fusable = old
+    assert calls['n'] > 50
+
+
 def test_reuse_on_off_and_unused_flows(oracle_ops):
     from refvsr_b200.synth import sliding_windows
     res = {}

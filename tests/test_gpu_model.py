@@ -58,6 +58,19 @@ def test_tensor_core_and_simt_paths_agree():
         assert psnr(a, b) >= 55.0
 
 
+def test_fused_resblock_path_matches_unfused():
+    """config.b200_fuse_resblocks=True routes every ResidualBlockNoBN / ResBlock through rv_resblock"""
+    name = 'mfid_t5_40x56_ref2x'
+    res = {}
+    for fuse in (True, False):
+        spec, cfg, net, lrs, refs, golden = build_case(name, 'cuda', b200_precision='fp16', b200_fuse_resblocks=fuse)
+        res[fuse] = run_clip(net, lrs, refs, spec['T'])
+    for k, (a, b) in enumerate(zip(res[True], res[False])):
+        g = torch.from_numpy(golden[f'result_{k}'])
+        print(f'fused window {k}: psnr vs unfused {psnr(a, b):.1f} dB, vs reference {psnr(a, g):.1f} dB')
+        assert psnr(a, b) >= 60.0 and psnr(a, g) >= 55.0
+
+
 def test_reuse_is_exact():
     """sliding-window reuse (flows / matches / ref features) must not change a single bit."""
     name = 'small_t7_24x32'
