@@ -145,7 +145,15 @@ __device__ __forceinline__ void issue_taps_box(uint32_t d_tmem, uint64_t ad, uin
   }
 }
 
-template <typename TI, typename TR, typename TO>
+// MODE: 0 = 128B-swizzled boxes per (kx, chunk); 1 = single box per (tile, chunk); 2 = 32B-swizzled quads per kx.
+// One instantiation per mode keeps the (register-critical) epilogue free of the other modes' code.
+#ifdef RV_CONV_EXPERIMENTS
+#define RV_DBG(p, bit) ((p).dbg & (bit))
+#else
+#define RV_DBG(p, bit) 0
+#endif
+
+template <typename TI, typename TR, typename TO, int MODE>
 __global__ void __launch_bounds__(64 + 128 * NACC, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                const TcP p) {
@@ -213,15 +221,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         int kx = 0, ch = 0;
         for (int s = 0; s < p.S; ++s) {
           tc::mbar_wait(&bar_empty[slot], ph ^ 1u);
-          if (p.dbg & 8) {
+          if (RV_DBG(p, 8)) {
             tc::mbar_arrive(&bar_full[slot]);
-            if (++ch == nchunks) { ch = 0; kx += p.single_box ? 0 : 1; }
+            if (++ch == nchunks) { ch = 0; kx += (MODE == 1) ? 0 : 1; }
             if (++slot == p.slots) { slot = 0; ph ^= 1u; }
             continue;
           }
           tc::mbar_expect_tx(&bar_full[slot], tx_bytes);
           uint8_t* dstA = smemA + (size_t)slot * p.a_bytes;
-          if (p.sw32) {
+          if constexpr (MODE == 2) {
             // stage = kx; one 16-channel box per quad of src0 | src1
             for (int qd = 0; qd < p.nq0 + p.nq1; ++qd) {
               if (qd < p.nq0)
@@ -234,15 +242,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
             ++kx;
             if (++slot == p.slots) { slot = 0; ph ^= 1u; }
             continue;
-          }
+          } else {
           if (ch < p.nch0)
             tc::tma_load_3d(&tm0, &bar_full[slot], dstA, ch * 64, xc + kx, yc);
           else
             tc::tma_load_3d(&tm1, &bar_full[slot], dstA, (ch - p.nch0) * 64, xc + kx, yc);
           if (!p.resident)
             tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_full[slot], smemW + (size_t)slot * p.w_bytes, p.w_bytes);
-          if (++ch == nchunks) { ch = 0; kx += p.single_box ? 0 : 1; }
+          if (++ch == nchunks) { ch = 0; kx += (MODE == 1) ? 0 : 1; }
           if (++slot == p.slots) { slot = 0; ph ^= 1u; }
+          }
         }
         tx0 += dtx; ty0 += dty;
         if (tx0 >= p.tiles_x) { tx0 -= p.tiles_x; ++ty0; }
@@ -256,7 +265,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       const uint32_t idesc = tc::umma_idesc(p.fmt, 128, p.NB);
       // SBO (bits [32,46)): 1024 B between 8-row groups in mode 0, bw*128 B (next tile row) in mode 1
       const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(smemA)) +
-                              (p.single_box ? ((uint64_t)((p.bw * 128 - 1024) >> 4) << 32) : 0ull);
+                              ((MODE == 1) ? ((uint64_t)((p.bw * 128 - 1024) >> 4) << 32) : 0ull);
       const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(smemW));
       const uint64_t adesc32 = tc::umma_desc_sw32(tc::smem_u32(smemA)), bdesc32 = tc::umma_desc_sw32(tc::smem_u32(smemW));
       const uint32_t a_step = p.a_bytes >> 4, w_step = p.w_bytes >> 4, b_tap = (uint32_t)(p.NB * 128) >> 4;
@@ -276,8 +285,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)(p.resident ? s : slot) * w_step);
           tc::mbar_wait(&bar_full[slot], ph);
           tc::tc_fence_after();
-          if (p.dbg & 1) {
-          } else if (p.sw32) {
+          if (RV_DBG(p, 1)) {
+          } else if constexpr (MODE == 2) {
             const uint64_t ad32 = adesc32 + (uint64_t)((uint32_t)slot * a_step);
             const uint64_t bd32 = bdesc32 + (uint64_t)((uint32_t)(p.resident ? s : slot) * w_step);
             const int nq = p.nq0 + p.nq1;
@@ -288,17 +297,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                              idesc, accumulate);
                 accumulate = 1;
               }
-          } else if (p.single_box) {
+          } else if constexpr (MODE == 1) {
             switch (p.kh) {
               case 1: issue_taps_box<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
               case 3: issue_taps_box<3>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
               case 5: issue_taps_box<5>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
               default: issue_taps_box<7>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
             }
-          } else
+          } else {
           switch (p.kh) {
             case 1: issue_taps<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
-            case 3: issue_taps<3>((p.dbg & 16) ? tmem_base : d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate, (p.dbg & 16) ? p.acc_stride : 0); break;
+            case 3: issue_taps<3>(RV_DBG(p, 16) ? tmem_base : d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate, RV_DBG(p, 16) ? p.acc_stride : 0); break;
             case 5: issue_taps<5>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
             case 7: issue_taps<7>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
             default:
@@ -307,6 +316,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                   tc::umma_f16(d_tmem, ad + (uint64_t)(ky * (TW * 128 / 16) + k * 2), bd + (uint64_t)(ky * b_tap + k * 2), idesc, accumulate);
                   accumulate = 1;
                 }
+          }
           }
           tc::umma_commit(&bar_empty[slot]);  // frees the smem slot when these MMAs retire
           if (++ch == nchunks) ch = 0;
@@ -341,7 +351,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
 #pragma unroll
       for (int c = 0; c < PRE; ++c) {
         const int n0 = nblk * p.NB + c * 16;
-        pre_ok[c] = valid && (c * 16 < p.NB) && (n0 + 16 <= p.cout) && p.vec_ok && !(p.dbg & 2);
+        pre_ok[c] = valid && (c * 16 < p.NB) && (n0 + 16 <= p.cout) && p.vec_ok && !RV_DBG(p, 2);
         if (pre_ok[c] && res != nullptr && sizeof(TR) == 2) {
           const uint4* q4 = reinterpret_cast<const uint4*>(res + pix * p.res_cs + n0);
           rp[c][0] = __ldg(q4);
@@ -361,11 +371,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         const int c0 = c * 16;
         if (c0 >= p.NB) break;
         const int n0 = nblk * p.NB + c0;
-        const bool live = valid && n0 < p.cout && !(p.dbg & 2);
+        const bool live = valid && n0 < p.cout && !RV_DBG(p, 2);
         const bool full = (n0 + 16 <= p.cout);
         const bool vec = full && p.vec_ok;
         const bool pre = (c < PRE) && pre_ok[c < PRE ? c : 0];
-        if (p.dbg & 4) continue;
+        if (RV_DBG(p, 4)) continue;
         float g[16], rr[16];
         if (live && gate) {
           if (pre) {
@@ -478,10 +488,10 @@ static int make_act_tmap(CUtensorMap* m, const void* ptr, int C, int W, int H, i
 static int g_num_sms = 0;
 static int g_max_smem = 0;
 
-template <typename TI, typename TR, typename TO>
-static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& p, dim3 grid, size_t smem,
+template <typename TI, typename TR, typename TO, int MODE>
+static int launch_tc_mode(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& p, dim3 grid, size_t smem,
                      cudaStream_t st) {
-  auto kern = conv_tc_kernel<TI, TR, TO>;
+  auto kern = conv_tc_kernel<TI, TR, TO, MODE>;
   static size_t configured = 0;   // per template instantiation
   if (smem > configured) {
     RV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -501,6 +511,13 @@ static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& 
   RV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm0, tm1, p));
   RV_LAUNCH_CHECK("conv_tc");
   return RV_OK;
+}
+
+template <typename TI, typename TR, typename TO>
+static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& p, dim3 grid, size_t smem, cudaStream_t st) {
+  if (p.sw32) return launch_tc_mode<TI, TR, TO, 2>(tm0, tm1, p, grid, smem, st);
+  if (p.single_box) return launch_tc_mode<TI, TR, TO, 1>(tm0, tm1, p, grid, smem, st);
+  return launch_tc_mode<TI, TR, TO, 0>(tm0, tm1, p, grid, smem, st);
 }
 
 int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
