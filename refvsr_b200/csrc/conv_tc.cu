@@ -28,7 +28,9 @@ namespace rv {
 
 static constexpr int TH = 8, TW = 16;
 static constexpr int MAX_SLOTS = 8;
-static constexpr int NACC = 3;  // TMEM accumulator buffers == epilogue warp groups
+static constexpr int NACC = 3;      // epilogue warp groups
+static constexpr int MAX_ACC = 6;   // TMEM accumulator buffers in flight (p.nacc = 3 or 6): the MMA warp may run this many
+                                    // tiles ahead of the epilogue groups; an accumulator is busy for MMA time + epilogue time
 
 struct TcP {
   int Ho, Wo, kh, kw, pad;
@@ -53,8 +55,12 @@ struct TcP {
   // layout 2: operands staged with SWIZZLE_32B in 16-channel quads (32-byte rows): one UMMA_K = 16 slice is a
   // whole row, so each tcgen05.mma fetches exactly its operand bytes (with 128-byte rows every K-slice pulls the
   // full row: ~110 cycles per MMA at N = 48, measured - profiles/r01_conv_knockout.md)
+  int nacc;                               // accumulator buffers in TMEM (3 or 6)
+  int dual;                               // two MMA-issuing warps (needs grp == S)
+  int grp;                                // consecutive stages that share one full/empty barrier pair (1 or S)
   int sw32, nq0, nq1;
   uint32_t q_bytes;                       // bytes of one quad sub-buffer of an A stage
+  long long* trace;                       // experiment hook: device timeline buffer (REFVSR_CONV_TRACE=<ptr>)
   int dbg;                                // experiment hook (REFVSR_CONV_DBG): 1 no MMA, 2 no epilogue global traffic,
                                           // 4 no TMEM loads, 8 no TMA box loads
 };
@@ -145,27 +151,81 @@ __device__ __forceinline__ void issue_taps_box(uint32_t d_tmem, uint64_t ad, uin
   }
 }
 
+// Tile-granular MMA issue loop (all S stages of a tile behind one full / empty barrier pair): issuer `id` of `n`
+// handles local tiles id, id + n, ...; tile tl uses smem slot tl % slots and TMEM accumulator tl % nacc.
+template <int MODE>
+__device__ __forceinline__ void mma_tiles(const TcP& p, int id, int n, int ntiles, int nchunks, uint32_t tmem_base, uint32_t idesc,
+                                          uint64_t adesc0, uint64_t bdesc0, uint64_t* bar_full, uint64_t* bar_empty,
+                                          uint64_t* bar_tfull, uint64_t* bar_tempty, uint64_t* bar_w) {
+  const uint32_t a_step = p.a_bytes >> 4, w_step = p.w_bytes >> 4, b_tap = (uint32_t)(p.NB * 128) >> 4;
+  const uint32_t q_step = p.q_bytes >> 4, bq = (uint32_t)(p.NB * 32) >> 4;
+  const int nq = p.nq0 + p.nq1;
+  tc::mbar_wait(bar_w, 0);
+  for (uint32_t tl = (uint32_t)id; (int)(blockIdx.x + tl * gridDim.x) < ntiles; tl += (uint32_t)n) {
+    const uint32_t slot = tl % (uint32_t)p.slots, ph = (tl / (uint32_t)p.slots) & 1u;
+    const uint32_t acc = tl % (uint32_t)p.nacc, accph = (tl / (uint32_t)p.nacc) & 1u;
+    const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+    tc::mbar_wait(&bar_tempty[acc], accph ^ 1u);
+    tc::mbar_wait(&bar_full[slot], ph);
+    tc::tc_fence_after();
+    uint32_t accumulate = 0;
+    uint64_t ad = adesc0 + (uint64_t)(slot * (uint32_t)p.grp * a_step);
+    uint64_t bd = bdesc0;
+    if constexpr (MODE == 2) {
+      for (int kx = 0; kx < p.kw; ++kx, ad += a_step, bd += w_step)
+        for (int ky = 0; ky < p.kh; ++ky)
+          for (int qd = 0; qd < nq; ++qd) {
+            tc::umma_f16(d_tmem, ad + (uint64_t)(qd * q_step + ky * (TW * 32 / 16)), bd + (uint64_t)((ky * nq + qd) * bq), idesc, accumulate);
+            accumulate = 1;
+          }
+    } else {
+      for (int kx = 0; kx < p.kw; ++kx)
+        for (int ch = 0; ch < nchunks; ++ch, ad += a_step, bd += w_step) {
+          const int crem = (ch < p.nch0) ? (p.c0 - ch * 64) : (p.c1 - (ch - p.nch0) * 64);
+          const int ksteps = (min(crem, 64) + 15) >> 4;
+          switch (p.kh) {
+            case 1: issue_taps<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
+            case 3: issue_taps<3>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
+            case 5: issue_taps<5>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
+            default: issue_taps<7>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
+          }
+        }
+    }
+    tc::umma_commit(&bar_empty[slot]);
+    tc::umma_commit(&bar_tfull[acc]);
+  }
+}
+
 // MODE: 0 = 128B-swizzled boxes per (kx, chunk); 1 = single box per (tile, chunk); 2 = 32B-swizzled quads per kx.
 // One instantiation per mode keeps the (register-critical) epilogue free of the other modes' code.
 #ifdef RV_CONV_EXPERIMENTS
 #define RV_DBG(p, bit) ((p).dbg & (bit))
+// device-side timeline of CTA 0: role r writes (event, tile, clock64) triples into its own region of p.trace
+#define RV_TRACE(role, ev, tile)                                                                   \
+  do {                                                                                             \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tr_n < 1000) {                 \
+      long long* _t = p.trace + ((size_t)(role) * 1000 + tr_n) * 3;                                \
+      _t[0] = (ev); _t[1] = (tile); _t[2] = clock64(); ++tr_n;                                     \
+    }                                                                                              \
+  } while (0)
 #else
 #define RV_DBG(p, bit) 0
+#define RV_TRACE(role, ev, tile) do { } while (0)
 #endif
 
 template <typename TI, typename TR, typename TO, int MODE>
-__global__ void __launch_bounds__(64 + 128 * NACC, 1)
+__global__ void __launch_bounds__(96 + 128 * NACC, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                const TcP p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_full[MAX_SLOTS], bar_empty[MAX_SLOTS], bar_w, bar_tfull[NACC], bar_tempty[NACC];
+  __shared__ uint64_t bar_full[MAX_SLOTS], bar_empty[MAX_SLOTS], bar_w, bar_tfull[MAX_ACC], bar_tempty[MAX_ACC];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[256];
 
   const uint32_t raw = tc::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* smemA = smem;
-  uint8_t* smemW = smem + (size_t)p.slots * p.a_bytes;
+  uint8_t* smemW = smem + (size_t)p.slots * p.grp * p.a_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = blockIdx.y;
@@ -183,7 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       tc::mbar_init(&bar_empty[i], 1);
     }
     tc::mbar_init(&bar_w, 1);
-    for (int i = 0; i < NACC; ++i) {
+    for (int i = 0; i < MAX_ACC; ++i) {
       tc::mbar_init(&bar_tfull[i], 1);
       tc::mbar_init(&bar_tempty[i], 4);
     }
@@ -214,21 +274,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       const uint32_t tx_bytes = p.a_bytes + (p.resident ? 0u : p.w_bytes);
       int slot = 0;
       uint32_t ph = 0;
+      int tr_n = 0; (void)tr_n;
       int ty0 = blockIdx.x / p.tiles_x, tx0 = blockIdx.x - ty0 * p.tiles_x;   // tile coordinates, advanced incrementally
       const int dty = gridDim.x / p.tiles_x, dtx = gridDim.x - dty * p.tiles_x;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int yc = ty0 * p.th - p.pad, xc = tx0 * p.tw - p.pad;
         int kx = 0, ch = 0;
-        for (int s = 0; s < p.S; ++s) {
-          tc::mbar_wait(&bar_empty[slot], ph ^ 1u);
+        for (int s = 0, sub = 0; s < p.S; ++s, sub = (sub + 1 == p.grp) ? 0 : sub + 1) {
+          const bool first_of_group = (sub == 0), last_of_group = (sub + 1 == p.grp);
+          RV_TRACE(0, 0, tile);
+          if (first_of_group) tc::mbar_wait(&bar_empty[slot], ph ^ 1u);
+          RV_TRACE(0, 1, tile);
           if (RV_DBG(p, 8)) {
             tc::mbar_arrive(&bar_full[slot]);
             if (++ch == nchunks) { ch = 0; kx += (MODE == 1) ? 0 : 1; }
             if (++slot == p.slots) { slot = 0; ph ^= 1u; }
             continue;
           }
-          tc::mbar_expect_tx(&bar_full[slot], tx_bytes);
-          uint8_t* dstA = smemA + (size_t)slot * p.a_bytes;
+          if (first_of_group) tc::mbar_expect_tx(&bar_full[slot], tx_bytes * (uint32_t)p.grp);
+          uint8_t* dstA = smemA + ((size_t)slot * p.grp + sub) * p.a_bytes;
           if constexpr (MODE == 2) {
             // stage = kx; one 16-channel box per quad of src0 | src1
             for (int qd = 0; qd < p.nq0 + p.nq1; ++qd) {
@@ -240,7 +304,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
             if (!p.resident)
               tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_full[slot], smemW + (size_t)slot * p.w_bytes, p.w_bytes);
             ++kx;
-            if (++slot == p.slots) { slot = 0; ph ^= 1u; }
+            if (last_of_group && ++slot == p.slots) { slot = 0; ph ^= 1u; }
             continue;
           } else {
           if (ch < p.nch0)
@@ -250,12 +314,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           if (!p.resident)
             tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_full[slot], smemW + (size_t)slot * p.w_bytes, p.w_bytes);
           if (++ch == nchunks) { ch = 0; kx += (MODE == 1) ? 0 : 1; }
-          if (++slot == p.slots) { slot = 0; ph ^= 1u; }
+          if (last_of_group && ++slot == p.slots) { slot = 0; ph ^= 1u; }
           }
         }
         tx0 += dtx; ty0 += dty;
         if (tx0 >= p.tiles_x) { tx0 -= p.tiles_x; ++ty0; }
       }
+    }
+  } else if (warp == 1 + 4 * NACC + 1) {
+    // ============================ second MMA issuer (tile-granular stages only) ==============================
+    // Device timelines (profiles/r01_conv_timeline.md) show the issuing thread is the critical resource: each
+    // tcgen05.mma issue holds it ~140 cycles and the epilogue groups idle 70 % of the time.  With whole tiles behind
+    // one barrier pair, two warps issue alternate tiles (separate smem slots and TMEM accumulators).
+    if (lane == 0 && p.dual) {
+      const uint32_t idesc = tc::umma_idesc(p.fmt, 128, p.NB);
+      const uint64_t adesc0 = (MODE == 2) ? tc::umma_desc_sw32(tc::smem_u32(smemA)) : tc::umma_desc_sw128(tc::smem_u32(smemA));
+      const uint64_t bdesc0 = (MODE == 2) ? tc::umma_desc_sw32(tc::smem_u32(smemW)) : tc::umma_desc_sw128(tc::smem_u32(smemW));
+      mma_tiles<MODE>(p, 1, 2, ntiles, nchunks, tmem_base, idesc, adesc0, bdesc0, bar_full, bar_empty, bar_tfull, bar_tempty, &bar_w);
+    }
+  } else if (warp == 1 && p.dual) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::umma_idesc(p.fmt, 128, p.NB);
+      const uint64_t adesc0 = (MODE == 2) ? tc::umma_desc_sw32(tc::smem_u32(smemA)) : tc::umma_desc_sw128(tc::smem_u32(smemA));
+      const uint64_t bdesc0 = (MODE == 2) ? tc::umma_desc_sw32(tc::smem_u32(smemW)) : tc::umma_desc_sw128(tc::smem_u32(smemW));
+      mma_tiles<MODE>(p, 0, 2, ntiles, nchunks, tmem_base, idesc, adesc0, bdesc0, bar_full, bar_empty, bar_tfull, bar_tempty, &bar_w);
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
@@ -272,22 +354,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       if (p.resident) tc::mbar_wait(&bar_w, 0);
       int slot = 0;
       uint32_t ph = 0, acc = 0, accph = 0;
+      int tr_n = 0; (void)tr_n;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        RV_TRACE(1, 0, tile);
         tc::mbar_wait(&bar_tempty[acc], accph ^ 1u);
         tc::tc_fence_after();
+        RV_TRACE(1, 1, tile);
         const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
         uint32_t accumulate = 0;
         int ch = 0;
-        for (int s = 0; s < p.S; ++s) {
+        for (int s = 0, sub = 0; s < p.S; ++s, sub = (sub + 1 == p.grp) ? 0 : sub + 1) {
           const int crem = (ch < p.nch0) ? (p.c0 - ch * 64) : (p.c1 - (ch - p.nch0) * 64);
           const int ksteps = (min(crem, 64) + 15) >> 4;
-          const uint64_t ad = adesc0 + (uint64_t)((uint32_t)slot * a_step);
+          const uint32_t abuf = (uint32_t)(slot * p.grp + sub);
+          const uint64_t ad = adesc0 + (uint64_t)(abuf * a_step);
           const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)(p.resident ? s : slot) * w_step);
-          tc::mbar_wait(&bar_full[slot], ph);
-          tc::tc_fence_after();
+          if (sub == 0) {
+            tc::mbar_wait(&bar_full[slot], ph);
+            tc::tc_fence_after();
+          }
+          RV_TRACE(1, 2, tile);
           if (RV_DBG(p, 1)) {
           } else if constexpr (MODE == 2) {
-            const uint64_t ad32 = adesc32 + (uint64_t)((uint32_t)slot * a_step);
+            const uint64_t ad32 = adesc32 + (uint64_t)(abuf * a_step);
             const uint64_t bd32 = bdesc32 + (uint64_t)((uint32_t)(p.resident ? s : slot) * w_step);
             const int nq = p.nq0 + p.nq1;
             const uint32_t q_step = p.q_bytes >> 4, bq = (uint32_t)(p.NB * 32) >> 4;
@@ -318,15 +407,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                 }
           }
           }
-          tc::umma_commit(&bar_empty[slot]);  // frees the smem slot when these MMAs retire
+          RV_TRACE(1, 3, tile);
           if (++ch == nchunks) ch = 0;
-          if (++slot == p.slots) { slot = 0; ph ^= 1u; }
+          if (sub + 1 == p.grp) {
+            tc::umma_commit(&bar_empty[slot]);
+            RV_TRACE(1, 4, tile);  // frees the smem slot (group of boxes) when these MMAs retire
+            if (++slot == p.slots) { slot = 0; ph ^= 1u; }
+          }
         }
         tc::umma_commit(&bar_tfull[acc]);
-        if (++acc == NACC) { acc = 0; accph ^= 1u; }
+        RV_TRACE(1, 5, tile);
+        if (++acc == (uint32_t)p.nacc) { acc = 0; accph ^= 1u; }
       }
     }
-  } else {
+  } else if (warp < 2 + 4 * NACC) {
     // ============================ epilogue ================================
     const int grp = (warp - 2) >> 2;  // accumulator buffer / tile parity owned by this group
     const int q = warp & 3;           // TMEM lane quarter this warp may access
@@ -338,10 +432,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     const float pre_slope = p.pre_slope, post_slope = p.post_slope;
     asm volatile("griddepcontrol.wait;" ::: "memory");     // gate / residual reads and all stores come after this
     constexpr int PRE = 3;  // chunks whose residual / gate vectors are prefetched before the accumulator wait
-    const uint32_t acc = (uint32_t)grp;
-    uint32_t accph = 0;
-    // group g owns accumulator g: tiles blockIdx.x + (g + NACC*i) * gridDim.x
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += NACC * gridDim.x, accph ^= 1u) {
+    // group g drains local tiles t = g, g + 3, g + 6, ...; tile t lives in accumulator t % nacc
+    uint32_t tl = (uint32_t)grp;
+    int tr_n = (q == 0 && lane == 0) ? 0 : 1000000; (void)tr_n;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += NACC * gridDim.x, tl += NACC) {
+      const uint32_t acc = tl % (uint32_t)p.nacc, accph = (tl / (uint32_t)p.nacc) & 1u;
       const int oy = (tile / p.tiles_x) * p.th + ty, ox = (tile % p.tiles_x) * p.tw + tx;
       const bool valid = (oy < p.Ho) && (ox < p.Wo);
       const size_t pix = (size_t)oy * p.Wo + ox;
@@ -363,8 +458,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           gp[c][1] = __ldg(q4 + 1);
         }
       }
+      RV_TRACE(2 + grp, 0, tile);
       tc::mbar_wait(&bar_tfull[acc], accph);
       tc::tc_fence_after();
+      RV_TRACE(2 + grp, 1, tile);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride;
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
@@ -404,6 +501,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         uint32_t r[16];
         tc::tmem_ld16(taddr + c0, r);
         tc::tmem_ld_wait();
+        RV_TRACE(2 + grp, 2, tile);
         if (!live) continue;
         float v[16];
 #pragma unroll
@@ -445,9 +543,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
             if (n0 + j < p.cout) out[pix * p.out_cs + n0 + j] = from_f<TO>(v[j]);
         }
       }
+      RV_TRACE(2 + grp, 3, tile);
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bar_tempty[acc]);
+      RV_TRACE(2 + grp, 4, tile);
     }
   }
 
@@ -499,7 +599,7 @@ static int launch_tc_mode(const CUtensorMap& tm0, const CUtensorMap& tm1, const 
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(64 + 128 * NACC);
+  cfg.blockDim = dim3(96 + 128 * NACC);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -574,10 +674,19 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   }
   { const char* e = getenv("REFVSR_BO_FORCE"); p.bo_force = e ? atoi(e) : -1; }
   { const char* e = getenv("REFVSR_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("REFVSR_CONV_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
   p.tiles_x = (p.Wo + p.tw - 1) / p.tw; p.tiles_y = (p.Ho + p.th - 1) / p.th;
   // shared-memory plan: weights resident when they leave room for >= 3 A slots
   const size_t w_all = (size_t)p.S * p.w_bytes;
-  if (p.single_box || w_all + 3 * (size_t)p.a_bytes <= budget) {
+  p.grp = 1;
+  static const bool group_stages = getenv("REFVSR_NO_STAGE_GROUPS") == nullptr;
+  if (group_stages && p.S > 1 && w_all + 2 * (size_t)p.S * p.a_bytes <= budget) {
+    // all stages of a tile behind ONE full / empty barrier pair: the MMA-issuing thread (the serial resource of
+    // the kernel) pays one wait + one tcgen05.commit per tile instead of one per stage
+    p.resident = 1;
+    p.grp = p.S;
+    p.slots = (int)std::min<size_t>(MAX_SLOTS, (budget - w_all) / ((size_t)p.S * p.a_bytes));
+  } else if (p.single_box || w_all + 3 * (size_t)p.a_bytes <= budget) {
     p.resident = 1;
     p.slots = (int)std::min<size_t>(MAX_SLOTS, (budget - w_all) / p.a_bytes);
   } else {
@@ -586,8 +695,8 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
     RV_REQUIRE(p.slots >= 2, "rv_conv2d(tc): stage of %u bytes does not fit twice in shared memory",
                p.a_bytes + p.w_bytes);
   }
-  p.slots = std::min(p.slots, std::max(2, p.single_box ? 6 * p.S : 3 * p.S));
-  const size_t smem = 1024 + (size_t)p.slots * p.a_bytes + (p.resident ? w_all : (size_t)p.slots * p.w_bytes);
+  if (p.grp == 1) p.slots = std::min(p.slots, std::max(2, p.single_box ? 6 * p.S : 3 * p.S));
+  const size_t smem = 1024 + (size_t)p.slots * p.grp * p.a_bytes + (p.resident ? w_all : (size_t)p.slots * p.w_bytes);
   p.wpack = (const uint8_t*)d->wpack; p.bias = d->bias;
   auto slope = [](int act) { return act == RV_ACT_RELU ? 0.f : act == RV_ACT_LRELU01 ? 0.1f : act == RV_ACT_LRELU02 ? 0.2f : 1.f; };
   RV_REQUIRE(d->act_pre != RV_ACT_CLAMP3, "rv_conv2d(tc): clamp3 is only supported as act_post");
@@ -601,7 +710,10 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   p.vec_ok = al16(d->out, d->out_cs, d->out_dtype) && al16(d->gate, d->gate_cs, d->in_dtype) && al16(d->res, d->res_cs, rdt);
   p.acc_stride = (uint32_t)p.NB;
   uint32_t cols = 32;
-  while (cols < (uint32_t)NACC * p.NB) cols <<= 1;
+  p.nacc = (6 * p.NB <= 512) ? 6 : 3;
+  static const bool dual_ok = getenv("REFVSR_NO_DUAL_MMA") == nullptr;
+  p.dual = (dual_ok && p.grp == p.S && p.S > 1 && p.resident && !p.single_box && p.slots >= 2 && p.nacc >= 2) ? 1 : 0;
+  while (cols < (uint32_t)p.nacc * p.NB) cols <<= 1;
   p.tmem_cols = cols;
 
   CUtensorMap tm0, tm1;
