@@ -29,6 +29,7 @@ namespace rv {
 static constexpr int TH = 8, TW = 16;
 static constexpr int MAX_SLOTS = 8;
 static constexpr int NACC = 3;      // epilogue warp groups
+static constexpr int MAX_MMA = 3;   // MMA-issuing warps (warps 1..3; warp 0 = TMA producer, warps 4..15 = epilogue)
 static constexpr int MAX_ACC = 6;   // TMEM accumulator buffers in flight (p.nacc = 3 or 6): the MMA warp may run this many
                                     // tiles ahead of the epilogue groups; an accumulator is busy for MMA time + epilogue time
 
@@ -56,7 +57,7 @@ struct TcP {
   // whole row, so each tcgen05.mma fetches exactly its operand bytes (with 128-byte rows every K-slice pulls the
   // full row: ~110 cycles per MMA at N = 48, measured - profiles/r01_conv_knockout.md)
   int nacc;                               // accumulator buffers in TMEM (3 or 6)
-  int dual;                               // two MMA-issuing warps (needs grp == S)
+  int nmma;                               // MMA-issuing warps in use (1..MAX_MMA), tiles dealt round-robin
   int grp;                                // consecutive stages that share one full/empty barrier pair (1 or S)
   int sw32, nq0, nq1;
   uint32_t q_bytes;                       // bytes of one quad sub-buffer of an A stage
@@ -109,16 +110,16 @@ __device__ __forceinline__ void store16(T* p, const float v[16]) {
 // start addresses advance by +2 (32 bytes) per K-slice and by one tile row block per tap.
 template <int KH>
 __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t idesc, int ksteps,
-                                           uint32_t b_tap, uint32_t& accumulate, uint32_t alt = 0) {
+                                           uint32_t b_tap, uint32_t acc0, uint32_t alt = 0) {
 #pragma unroll
   for (int ky = 0; ky < KH; ++ky) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (k < ksteps) {
         // alt != 0 (timing experiment only): consecutive MMAs hit different accumulators -> no RAW chain on D
+        // acc0 = 0 only for the first stage of a tile: its first MMA overwrites the accumulator
         tc::umma_f16(d_tmem + (((ky * 4 + k) % 3) * alt), ad + (uint64_t)(ky * (TW * 128 / 16) + k * 2),
-                     bd + (uint64_t)(ky * b_tap + k * 2), idesc, accumulate);
-        accumulate = 1;
+                     bd + (uint64_t)(ky * b_tap + k * 2), idesc, (ky | k) ? 1u : acc0);
       }
     }
   }
@@ -129,8 +130,8 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint64_t ad, uint64_
 // then not 1024-byte aligned, which is fine: see the base_offset note below.
 template <int KH>
 __device__ __forceinline__ void issue_taps_box(uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t idesc, int ksteps,
-                                               uint32_t b_tap, int bw, int bo_force, uint32_t& accumulate) {
-#pragma unroll
+                                               uint32_t b_tap, int bw, int bo_force, uint32_t acc0) {
+#pragma unroll 1
   for (int ky = 0; ky < KH; ++ky) {
 #pragma unroll
     for (int kx = 0; kx < KH; ++kx) {
@@ -143,56 +144,10 @@ __device__ __forceinline__ void issue_taps_box(uint32_t d_tmem, uint64_t ad, uin
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (k < ksteps) {
-          tc::umma_f16(d_tmem, a_tap + (uint64_t)(k * 2), b_t + (uint64_t)(k * 2), idesc, accumulate);
-          accumulate = 1;
+          tc::umma_f16(d_tmem, a_tap + (uint64_t)(k * 2), b_t + (uint64_t)(k * 2), idesc, (ky | kx | k) ? 1u : acc0);
         }
       }
     }
-  }
-}
-
-// Tile-granular MMA issue loop (all S stages of a tile behind one full / empty barrier pair): issuer `id` of `n`
-// handles local tiles id, id + n, ...; tile tl uses smem slot tl % slots and TMEM accumulator tl % nacc.
-template <int MODE>
-__device__ __forceinline__ void mma_tiles(const TcP& p, int id, int n, int ntiles, int nchunks, uint32_t tmem_base, uint32_t idesc,
-                                          uint64_t adesc0, uint64_t bdesc0, uint64_t* bar_full, uint64_t* bar_empty,
-                                          uint64_t* bar_tfull, uint64_t* bar_tempty, uint64_t* bar_w) {
-  const uint32_t a_step = p.a_bytes >> 4, w_step = p.w_bytes >> 4, b_tap = (uint32_t)(p.NB * 128) >> 4;
-  const uint32_t q_step = p.q_bytes >> 4, bq = (uint32_t)(p.NB * 32) >> 4;
-  const int nq = p.nq0 + p.nq1;
-  tc::mbar_wait(bar_w, 0);
-  for (uint32_t tl = (uint32_t)id; (int)(blockIdx.x + tl * gridDim.x) < ntiles; tl += (uint32_t)n) {
-    const uint32_t slot = tl % (uint32_t)p.slots, ph = (tl / (uint32_t)p.slots) & 1u;
-    const uint32_t acc = tl % (uint32_t)p.nacc, accph = (tl / (uint32_t)p.nacc) & 1u;
-    const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-    tc::mbar_wait(&bar_tempty[acc], accph ^ 1u);
-    tc::mbar_wait(&bar_full[slot], ph);
-    tc::tc_fence_after();
-    uint32_t accumulate = 0;
-    uint64_t ad = adesc0 + (uint64_t)(slot * (uint32_t)p.grp * a_step);
-    uint64_t bd = bdesc0;
-    if constexpr (MODE == 2) {
-      for (int kx = 0; kx < p.kw; ++kx, ad += a_step, bd += w_step)
-        for (int ky = 0; ky < p.kh; ++ky)
-          for (int qd = 0; qd < nq; ++qd) {
-            tc::umma_f16(d_tmem, ad + (uint64_t)(qd * q_step + ky * (TW * 32 / 16)), bd + (uint64_t)((ky * nq + qd) * bq), idesc, accumulate);
-            accumulate = 1;
-          }
-    } else {
-      for (int kx = 0; kx < p.kw; ++kx)
-        for (int ch = 0; ch < nchunks; ++ch, ad += a_step, bd += w_step) {
-          const int crem = (ch < p.nch0) ? (p.c0 - ch * 64) : (p.c1 - (ch - p.nch0) * 64);
-          const int ksteps = (min(crem, 64) + 15) >> 4;
-          switch (p.kh) {
-            case 1: issue_taps<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
-            case 3: issue_taps<3>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
-            case 5: issue_taps<5>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
-            default: issue_taps<7>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
-          }
-        }
-    }
-    tc::umma_commit(&bar_empty[slot]);
-    tc::umma_commit(&bar_tfull[acc]);
   }
 }
 
@@ -203,7 +158,7 @@ __device__ __forceinline__ void mma_tiles(const TcP& p, int id, int n, int ntile
 // device-side timeline of CTA 0: role r writes (event, tile, clock64) triples into its own region of p.trace
 #define RV_TRACE(role, ev, tile)                                                                   \
   do {                                                                                             \
-    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tr_n < 1000) {                 \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tr_n < 1000 && ((threadIdx.x & 31) == 0 || (role) >= 2)) {                 \
       long long* _t = p.trace + ((size_t)(role) * 1000 + tr_n) * 3;                                \
       _t[0] = (ev); _t[1] = (tile); _t[2] = clock64(); ++tr_n;                                     \
     }                                                                                              \
@@ -214,7 +169,7 @@ __device__ __forceinline__ void mma_tiles(const TcP& p, int id, int n, int ntile
 #endif
 
 template <typename TI, typename TR, typename TO, int MODE>
-__global__ void __launch_bounds__(96 + 128 * NACC, 1)
+__global__ void __launch_bounds__(32 * (1 + MAX_MMA) + 128 * NACC, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                const TcP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -228,6 +183,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   uint8_t* smemW = smem + (size_t)p.slots * p.grp * p.a_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // same value, provably warp-uniform for the compiler
   const int nblk = blockIdx.y;
   const int ntiles = p.tiles_x * p.tiles_y;
   const int nchunks = p.nch0 + p.nch1;
@@ -251,7 +207,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     tc::prefetch_tmap(&tm0);
     if (p.nch1) tc::prefetch_tmap(&tm1);
   }
-  if (warp == 2) tc::tmem_alloc(&tmem_base_s, p.tmem_cols);
+  if (warp == 1 + MAX_MMA) tc::tmem_alloc(&tmem_base_s, p.tmem_cols);
   for (int i = threadIdx.x; i < p.NB; i += blockDim.x) {
     int n = nblk * p.NB + i;
     bias_s[i] = (n < p.cout) ? p.bias[n] : 0.f;
@@ -261,15 +217,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 0) {
+  // Register re-balancing (512 threads x 128 registers at launch): the four single-thread role warps (warpgroup 0)
+  // hand registers to the three epilogue warpgroups, whose 16-column drain + prefetch loop otherwise spills.
+  if (warp_u < 1 + MAX_MMA) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;" ::: "memory");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 144;" ::: "memory");
+
+  if (warp_u == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
+    // warp-uniform control flow (all lanes wait on the barriers), one elected lane issues the copies
+    {
       const uint8_t* wsrc = p.wpack + (size_t)nblk * p.S * p.w_bytes;
-      if (p.resident) {
+      if (p.resident && tc::elect_one()) {
         tc::mbar_expect_tx(&bar_w, (uint32_t)p.S * p.w_bytes);
         for (int s = 0; s < p.S; ++s)
           tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_w, smemW + (size_t)s * p.w_bytes, p.w_bytes);
       }
+      __syncwarp();
       asm volatile("griddepcontrol.wait;" ::: "memory");   // activations of the previous kernel are now visible
       const uint32_t tx_bytes = p.a_bytes + (p.resident ? 0u : p.w_bytes);
       int slot = 0;
@@ -280,90 +243,81 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int yc = ty0 * p.th - p.pad, xc = tx0 * p.tw - p.pad;
         int kx = 0, ch = 0;
-        for (int s = 0, sub = 0; s < p.S; ++s, sub = (sub + 1 == p.grp) ? 0 : sub + 1) {
-          const bool first_of_group = (sub == 0), last_of_group = (sub + 1 == p.grp);
+        for (int s = 0, sub = 0; s < p.S; ++s) {
           RV_TRACE(0, 0, tile);
-          if (first_of_group) tc::mbar_wait(&bar_empty[slot], ph ^ 1u);
+          if (sub == 0) tc::mbar_wait(&bar_empty[slot], ph ^ 1u);
           RV_TRACE(0, 1, tile);
-          if (RV_DBG(p, 8)) {
-            tc::mbar_arrive(&bar_full[slot]);
-            if (++ch == nchunks) { ch = 0; kx += (MODE == 1) ? 0 : 1; }
-            if (++slot == p.slots) { slot = 0; ph ^= 1u; }
-            continue;
-          }
-          if (first_of_group) tc::mbar_expect_tx(&bar_full[slot], tx_bytes * (uint32_t)p.grp);
-          uint8_t* dstA = smemA + ((size_t)slot * p.grp + sub) * p.a_bytes;
-          if constexpr (MODE == 2) {
-            // stage = kx; one 16-channel box per quad of src0 | src1
-            for (int qd = 0; qd < p.nq0 + p.nq1; ++qd) {
-              if (qd < p.nq0)
-                tc::tma_load_3d(&tm0, &bar_full[slot], dstA + (size_t)qd * p.q_bytes, qd * 16, xc + kx, yc);
-              else
-                tc::tma_load_3d(&tm1, &bar_full[slot], dstA + (size_t)qd * p.q_bytes, (qd - p.nq0) * 16, xc + kx, yc);
+          if (tc::elect_one()) {
+            if (RV_DBG(p, 8)) {
+              if (sub + 1 == p.grp) tc::mbar_arrive(&bar_full[slot]);
+            } else {
+              if (sub == 0) tc::mbar_expect_tx(&bar_full[slot], tx_bytes * (uint32_t)p.grp);
+              uint8_t* dstA = smemA + ((size_t)slot * p.grp + sub) * p.a_bytes;
+              if constexpr (MODE == 2) {
+                // stage = kx; one 16-channel box per quad of src0 | src1
+                for (int qd = 0; qd < p.nq0 + p.nq1; ++qd) {
+                  if (qd < p.nq0)
+                    tc::tma_load_3d(&tm0, &bar_full[slot], dstA + (size_t)qd * p.q_bytes, qd * 16, xc + kx, yc);
+                  else
+                    tc::tma_load_3d(&tm1, &bar_full[slot], dstA + (size_t)qd * p.q_bytes, (qd - p.nq0) * 16, xc + kx, yc);
+                }
+              } else {
+                if (ch < p.nch0)
+                  tc::tma_load_3d(&tm0, &bar_full[slot], dstA, ch * 64, xc + kx, yc);
+                else
+                  tc::tma_load_3d(&tm1, &bar_full[slot], dstA, (ch - p.nch0) * 64, xc + kx, yc);
+              }
+              if (!p.resident)
+                tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_full[slot], smemW + (size_t)slot * p.w_bytes, p.w_bytes);
             }
-            if (!p.resident)
-              tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_full[slot], smemW + (size_t)slot * p.w_bytes, p.w_bytes);
-            ++kx;
-            if (last_of_group && ++slot == p.slots) { slot = 0; ph ^= 1u; }
-            continue;
-          } else {
-          if (ch < p.nch0)
-            tc::tma_load_3d(&tm0, &bar_full[slot], dstA, ch * 64, xc + kx, yc);
-          else
-            tc::tma_load_3d(&tm1, &bar_full[slot], dstA, (ch - p.nch0) * 64, xc + kx, yc);
-          if (!p.resident)
-            tc::bulk_load(wsrc + (size_t)s * p.w_bytes, &bar_full[slot], smemW + (size_t)slot * p.w_bytes, p.w_bytes);
-          if (++ch == nchunks) { ch = 0; kx += (MODE == 1) ? 0 : 1; }
-          if (last_of_group && ++slot == p.slots) { slot = 0; ph ^= 1u; }
+          }
+          __syncwarp();
+          // stage order: mode 0 = (kx, chunk), mode 1 = (chunk), mode 2 = (kx)
+          if (MODE == 2) ++kx;
+          else if (++ch == nchunks) { ch = 0; kx += (MODE == 1) ? 0 : 1; }
+          if (++sub == p.grp) {
+            sub = 0;
+            if (++slot == p.slots) { slot = 0; ph ^= 1u; }
           }
         }
         tx0 += dtx; ty0 += dty;
         if (tx0 >= p.tiles_x) { tx0 -= p.tiles_x; ++ty0; }
       }
     }
-  } else if (warp == 1 + 4 * NACC + 1) {
-    // ============================ second MMA issuer (tile-granular stages only) ==============================
-    // Device timelines (profiles/r01_conv_timeline.md) show the issuing thread is the critical resource: each
-    // tcgen05.mma issue holds it ~140 cycles and the epilogue groups idle 70 % of the time.  With whole tiles behind
-    // one barrier pair, two warps issue alternate tiles (separate smem slots and TMEM accumulators).
-    if (lane == 0 && p.dual) {
-      const uint32_t idesc = tc::umma_idesc(p.fmt, 128, p.NB);
-      const uint64_t adesc0 = (MODE == 2) ? tc::umma_desc_sw32(tc::smem_u32(smemA)) : tc::umma_desc_sw128(tc::smem_u32(smemA));
-      const uint64_t bdesc0 = (MODE == 2) ? tc::umma_desc_sw32(tc::smem_u32(smemW)) : tc::umma_desc_sw128(tc::smem_u32(smemW));
-      mma_tiles<MODE>(p, 1, 2, ntiles, nchunks, tmem_base, idesc, adesc0, bdesc0, bar_full, bar_empty, bar_tfull, bar_tempty, &bar_w);
-    }
-  } else if (warp == 1 && p.dual) {
-    if (lane == 0) {
-      const uint32_t idesc = tc::umma_idesc(p.fmt, 128, p.NB);
-      const uint64_t adesc0 = (MODE == 2) ? tc::umma_desc_sw32(tc::smem_u32(smemA)) : tc::umma_desc_sw128(tc::smem_u32(smemA));
-      const uint64_t bdesc0 = (MODE == 2) ? tc::umma_desc_sw32(tc::smem_u32(smemW)) : tc::umma_desc_sw128(tc::smem_u32(smemW));
-      mma_tiles<MODE>(p, 0, 2, ntiles, nchunks, tmem_base, idesc, adesc0, bdesc0, bar_full, bar_empty, bar_tfull, bar_tempty, &bar_w);
-    }
-  } else if (warp == 1) {
-    // ============================ MMA issuer ==============================
-    // One thread issues every tcgen05.mma of the CTA, so its instruction stream is kept minimal:
+  } else if (warp_u < 1 + MAX_MMA) {
+    // ============================ MMA issuers ==============================
+    // Device timelines (profiles/r01_conv_timeline.md) show the issuing THREAD is the critical resource of this
+    // kernel: every tcgen05.mma holds it ~140 cycles while the tensor pipe and the epilogue groups idle.  So up to
+    // MAX_MMA warps issue, each owning the local tiles id, id + nmma, ... (own smem slots, own TMEM accumulator);
+    // the tensor pipe interleaves the independent instruction streams.  Per thread the stream is kept minimal:
     // descriptors are 64-bit bases plus small immediates, the tap loop is unrolled per kernel height.
-    if (lane == 0) {
+    const int id = warp_u - 1;
+    // warp-uniform control flow: all 32 lanes run the loop, an elected lane issues (see tc::umma_f16_elect)
+    if (id < p.nmma) {
       const uint32_t idesc = tc::umma_idesc(p.fmt, 128, p.NB);
       // SBO (bits [32,46)): 1024 B between 8-row groups in mode 0, bw*128 B (next tile row) in mode 1
-      const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(smemA)) +
-                              ((MODE == 1) ? ((uint64_t)((p.bw * 128 - 1024) >> 4) << 32) : 0ull);
-      const uint64_t bdesc0 = tc::umma_desc_sw128(tc::smem_u32(smemW));
-      const uint64_t adesc32 = tc::umma_desc_sw32(tc::smem_u32(smemA)), bdesc32 = tc::umma_desc_sw32(tc::smem_u32(smemW));
+      const uint64_t adesc0 = (MODE == 2) ? tc::umma_desc_sw32(tc::smem_u32(smemA))
+                                          : tc::umma_desc_sw128(tc::smem_u32(smemA)) +
+                                                ((MODE == 1) ? ((uint64_t)((p.bw * 128 - 1024) >> 4) << 32) : 0ull);
+      const uint64_t bdesc0 = (MODE == 2) ? tc::umma_desc_sw32(tc::smem_u32(smemW)) : tc::umma_desc_sw128(tc::smem_u32(smemW));
       const uint32_t a_step = p.a_bytes >> 4, w_step = p.w_bytes >> 4, b_tap = (uint32_t)(p.NB * 128) >> 4;
+      const uint32_t ngrp = (uint32_t)(p.S / p.grp);   // barrier groups (smem slots) per tile: 1 or S
       if (p.resident) tc::mbar_wait(&bar_w, 0);
-      int slot = 0;
-      uint32_t ph = 0, acc = 0, accph = 0;
       int tr_n = 0; (void)tr_n;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        RV_TRACE(1, 0, tile);
+      const int trole = (id == 0) ? 1 : 4 + id; (void)trole;
+      uint32_t tl = (uint32_t)id;
+      for (int tile = blockIdx.x + id * gridDim.x; tile < ntiles; tile += p.nmma * gridDim.x, tl += (uint32_t)p.nmma) {
+        const uint32_t g0 = tl * ngrp;
+        int slot = (int)(g0 % (uint32_t)p.slots);
+        uint32_t ph = (g0 / (uint32_t)p.slots) & 1u;
+        const uint32_t acc = tl % (uint32_t)p.nacc, accph = (tl / (uint32_t)p.nacc) & 1u;
+        RV_TRACE(trole, 0, tile);
         tc::mbar_wait(&bar_tempty[acc], accph ^ 1u);
         tc::tc_fence_after();
-        RV_TRACE(1, 1, tile);
+        RV_TRACE(trole, 1, tile);
         const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
-        uint32_t accumulate = 0;
         int ch = 0;
-        for (int s = 0, sub = 0; s < p.S; ++s, sub = (sub + 1 == p.grp) ? 0 : sub + 1) {
+        for (int s = 0, sub = 0; s < p.S; ++s) {
           const int crem = (ch < p.nch0) ? (p.c0 - ch * 64) : (p.c1 - (ch - p.nch0) * 64);
           const int ksteps = (min(crem, 64) + 15) >> 4;
           const uint32_t abuf = (uint32_t)(slot * p.grp + sub);
@@ -373,56 +327,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
             tc::mbar_wait(&bar_full[slot], ph);
             tc::tc_fence_after();
           }
-          RV_TRACE(1, 2, tile);
+          RV_TRACE(trole, 2, tile);
+          if (tc::elect_one()) {
           if (RV_DBG(p, 1)) {
           } else if constexpr (MODE == 2) {
-            const uint64_t ad32 = adesc32 + (uint64_t)(abuf * a_step);
-            const uint64_t bd32 = bdesc32 + (uint64_t)((uint32_t)(p.resident ? s : slot) * w_step);
             const int nq = p.nq0 + p.nq1;
             const uint32_t q_step = p.q_bytes >> 4, bq = (uint32_t)(p.NB * 32) >> 4;
             for (int ky = 0; ky < p.kh; ++ky)
               for (int qd = 0; qd < nq; ++qd) {
-                tc::umma_f16(d_tmem, ad32 + (uint64_t)(qd * q_step + ky * (TW * 32 / 16)), bd32 + (uint64_t)((ky * nq + qd) * bq),
-                             idesc, accumulate);
-                accumulate = 1;
+                tc::umma_f16(d_tmem, ad + (uint64_t)(qd * q_step + ky * (TW * 32 / 16)), bd + (uint64_t)((ky * nq + qd) * bq),
+                             idesc, (s | ky | qd) ? 1u : 0u);
               }
           } else if constexpr (MODE == 1) {
             switch (p.kh) {
-              case 1: issue_taps_box<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
-              case 3: issue_taps_box<3>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
-              case 5: issue_taps_box<5>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
-              default: issue_taps_box<7>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, accumulate); break;
+              case 1: issue_taps_box<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, s ? 1u : 0u); break;
+              case 3: issue_taps_box<3>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, s ? 1u : 0u); break;
+              case 5: issue_taps_box<5>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, s ? 1u : 0u); break;
+              default: issue_taps_box<7>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, s ? 1u : 0u); break;
             }
           } else {
-          switch (p.kh) {
-            case 1: issue_taps<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
-            case 3: issue_taps<3>(RV_DBG(p, 16) ? tmem_base : d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate, RV_DBG(p, 16) ? p.acc_stride : 0); break;
-            case 5: issue_taps<5>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
-            case 7: issue_taps<7>(d_tmem, ad, bd, idesc, ksteps, b_tap, accumulate); break;
-            default:
-              for (int ky = 0; ky < p.kh; ++ky)
-                for (int k = 0; k < ksteps; ++k) {
-                  tc::umma_f16(d_tmem, ad + (uint64_t)(ky * (TW * 128 / 16) + k * 2), bd + (uint64_t)(ky * b_tap + k * 2), idesc, accumulate);
-                  accumulate = 1;
-                }
+            switch (p.kh) {
+              case 1: issue_taps<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, s ? 1u : 0u); break;
+              case 3: issue_taps<3>(RV_DBG(p, 16) ? tmem_base : d_tmem, ad, bd, idesc, ksteps, b_tap, s ? 1u : 0u, RV_DBG(p, 16) ? p.acc_stride : 0); break;
+              case 5: issue_taps<5>(d_tmem, ad, bd, idesc, ksteps, b_tap, s ? 1u : 0u); break;
+              case 7: issue_taps<7>(d_tmem, ad, bd, idesc, ksteps, b_tap, s ? 1u : 0u); break;
+              default:
+                for (int ky = 0; ky < p.kh; ++ky)
+                  for (int k = 0; k < ksteps; ++k) {
+                    tc::umma_f16(d_tmem, ad + (uint64_t)(ky * (TW * 128 / 16) + k * 2), bd + (uint64_t)(ky * b_tap + k * 2), idesc, (s | ky | k) ? 1u : 0u);
+                  }
+            }
           }
+          if (sub + 1 == p.grp) tc::umma_commit(&bar_empty[slot]);   // frees the smem slot when these MMAs retire
+          if (s + 1 == p.S) tc::umma_commit(&bar_tfull[acc]);        // accumulator complete -> epilogue group
           }
-          RV_TRACE(1, 3, tile);
+          __syncwarp();
+          RV_TRACE(trole, 3, tile);
           if (++ch == nchunks) ch = 0;
-          if (sub + 1 == p.grp) {
-            tc::umma_commit(&bar_empty[slot]);
-            RV_TRACE(1, 4, tile);  // frees the smem slot (group of boxes) when these MMAs retire
+          if (++sub == p.grp) {
+            sub = 0;
             if (++slot == p.slots) { slot = 0; ph ^= 1u; }
           }
         }
-        tc::umma_commit(&bar_tfull[acc]);
-        RV_TRACE(1, 5, tile);
-        if (++acc == (uint32_t)p.nacc) { acc = 0; accph ^= 1u; }
+        RV_TRACE(trole, 5, tile);
       }
     }
-  } else if (warp < 2 + 4 * NACC) {
+  } else {
     // ============================ epilogue ================================
-    const int grp = (warp - 2) >> 2;  // accumulator buffer / tile parity owned by this group
+    const int grp = (warp - 1 - MAX_MMA) >> 2;  // accumulator buffer / tile parity owned by this group
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
     const int ty = m >> p.tw_shift, tx = m & (p.tw - 1);
@@ -553,7 +505,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
 
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == 1 + MAX_MMA) tc::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 PFN_tmapEncodeTiled get_tmap_encoder() {
@@ -599,7 +551,7 @@ static int launch_tc_mode(const CUtensorMap& tm0, const CUtensorMap& tm1, const 
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(96 + 128 * NACC);
+  cfg.blockDim = dim3(32 * (1 + MAX_MMA) + 128 * NACC);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -711,8 +663,11 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   p.acc_stride = (uint32_t)p.NB;
   uint32_t cols = 32;
   p.nacc = (6 * p.NB <= 512) ? 6 : 3;
-  static const bool dual_ok = getenv("REFVSR_NO_DUAL_MMA") == nullptr;
-  p.dual = (dual_ok && p.grp == p.S && p.S > 1 && p.resident && !p.single_box && p.slots >= 2 && p.nacc >= 2) ? 1 : 0;
+  // issuers: as many as there are whole tiles in flight in shared memory (and accumulators to write to)
+  static const int nmma_env = getenv("REFVSR_NMMA") ? atoi(getenv("REFVSR_NMMA")) : 0;
+  // (an issuer further ahead than the shared-memory ring would alias mbarrier phases, so this is a hard limit)
+  p.nmma = std::max(1, std::min(std::min((int)MAX_MMA, p.slots * p.grp / p.S), p.nacc));
+  if (nmma_env > 0) p.nmma = std::min(p.nmma, nmma_env);
   while (cols < (uint32_t)p.nacc * p.NB) cols <<= 1;
   p.tmem_cols = cols;
 

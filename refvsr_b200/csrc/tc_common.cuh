@@ -42,9 +42,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// The spin loop lives INSIDE the asm block: a C++ `while (!try_wait)` is a divergent loop to the compiler, after which
+// it no longer treats warp-uniform values (UMMA descriptors, barrier addresses) as uniform.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "RV_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra RV_DONE;\n\t"
+      "bra RV_WAIT;\n\t"
+      "RV_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
 }
 
 // ---- TMA ---------------------------------------------------------------------------------------
@@ -104,6 +113,17 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// One elected lane of a fully converged warp.  tcgen05.mma / commit are issued as
+//   if (tc::elect_one()) { umma_f16(...); ... }
+// from WARP-UNIFORM control flow with warp-uniform operands: the compiler then keeps the descriptors in uniform
+// registers and emits back-to-back UTCHMMA.  Issued from an `if (lane == 0)` branch it cannot prove uniformity and
+// wraps every MMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~27 SASS instructions, ~140 cycles per MMA
+// measured on B200 - profiles/r01_conv_timeline.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
