@@ -88,7 +88,11 @@ typedef struct rv_conv_desc {
   int32_t nb;            /* TC: output channels per CTA column block (packing.py decides) */
   int32_t k_real;        /* SIMT: rows of wpack = kh*kw*(c0+c1)                           */
   int32_t layout;        /* TC: 0 = [nblk][kx][chunk][ky][NB][64] (one TMA box per kx),    */
-                         /*     1 = [nblk][chunk][ky][kx][NB][64] (one box per tile+chunk) */
+                         /*     1 = [nblk][chunk][ky][kx][NB][64] (one box per tile+chunk; */
+                         /*         3x3 convs with the all-16-bit epilogue run kx-folded,  */
+                         /*         N = 3*NB per MMA),                                     */
+                         /*     2 = 32B-swizzled 16-channel quads,                         */
+                         /*     3 = weight image of 1, kx-folding disabled (test / A-B)    */
 } rv_conv_desc;
 
 int rv_conv2d(const rv_conv_desc* d, void* stream);

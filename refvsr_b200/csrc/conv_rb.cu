@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(448, 1) conv_rb_kernel(const __grid_constant__
   uint8_t* smMid = smIn + 2 * RB_IN_BYTES;       // 1 buffer (+ slack rows read by the garbage M rows of conv1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // provably warp-uniform copy for the role dispatch
   const int ntiles = p.tiles_x * p.tiles_y;
   const int ksteps = (min(p.C, 64) + 15) >> 4;
 
@@ -92,26 +93,31 @@ __global__ void __launch_bounds__(448, 1) conv_rb_kernel(const __grid_constant__
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t set_stride = 3u * (uint32_t)p.NB;   // {D1 tile0, D1 tile1, D2}
 
-  if (warp == 0) {
+  // Producer and MMA warps: warp-uniform control flow, one elected lane issues (see tc::elect_one).
+  if (warp_u == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(&bar_w, 2u * p.w_bytes);
       tc::bulk_load(p.w1, &bar_w, smW1, p.w_bytes);
       tc::bulk_load(p.w2, &bar_w, smW2, p.w_bytes);
-      asm volatile("griddepcontrol.wait;" ::: "memory");
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int slot = it & 1;
-        const uint32_t ph = (it >> 1) & 1u;
-        tc::mbar_wait(&bar_in_empty[slot], ph ^ 1u);
+    }
+    __syncwarp();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int slot = it & 1;
+      const uint32_t ph = (it >> 1) & 1u;
+      tc::mbar_wait(&bar_in_empty[slot], ph ^ 1u);
+      if (tc::elect_one()) {
         tc::mbar_expect_tx(&bar_in_full[slot], RB_IN_BYTES);
         const int ty0 = tile / p.tiles_x, tx0 = tile - ty0 * p.tiles_x;
         tc::tma_load_3d(&tmx, &bar_in_full[slot], smIn + (size_t)slot * RB_IN_BYTES, 0, tx0 * RB_TW - 2, ty0 * RB_TH - 2);
       }
+      __syncwarp();
     }
-  } else if (warp == 1) {
+  } else if (warp_u == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
       const uint32_t idesc = tc::umma_idesc(p.fmt, 128, p.NB);
       const uint64_t in_desc0 = tc::umma_desc_sw128(tc::smem_u32(smIn));                     // SBO 1024
       const uint64_t mid_desc = tc::umma_desc_sw128(tc::smem_u32(smMid)) +
@@ -127,24 +133,24 @@ __global__ void __launch_bounds__(448, 1) conv_rb_kernel(const __grid_constant__
         tc::mbar_wait(&bar_in_full[slot], ph);
         tc::mbar_wait(&bar_d1_empty[slot], ph ^ 1u);
         tc::tc_fence_after();
-        const uint64_t a0 = in_desc0 + (uint64_t)((uint32_t)slot * (RB_IN_BYTES >> 4));
-        const uint32_t d0 = tmem_base + (uint32_t)slot * set_stride;
+        if (tc::elect_one()) {
+          const uint64_t a0 = in_desc0 + (uint64_t)((uint32_t)slot * (RB_IN_BYTES >> 4));
+          const uint32_t d0 = tmem_base + (uint32_t)slot * set_stride;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint32_t accumulate = 0;
+          for (int j = 0; j < 2; ++j) {
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
+            for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
+              for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < ksteps) {
-                  tc::umma_f16(d0 + (uint32_t)j * p.NB, a0 + (uint64_t)((j * 128 + ky * RB_P + kx) * 8 + k * 2),
-                               w1_desc + (uint64_t)((ky * 3 + kx) * b_tap + k * 2), idesc, accumulate);
-                  accumulate = 1;
-                }
+                for (int k = 0; k < 4; ++k)
+                  if (k < ksteps)
+                    tc::umma_f16(d0 + (uint32_t)j * p.NB, a0 + (uint64_t)((j * 128 + ky * RB_P + kx) * 8 + k * 2),
+                                 w1_desc + (uint64_t)((ky * 3 + kx) * b_tap + k * 2), idesc, (ky | kx | k) ? 1u : 0u);
+          }
+          tc::umma_commit(&bar_d1_full[slot]);
         }
-        tc::umma_commit(&bar_d1_full[slot]);
+        __syncwarp();
       };
       auto conv2 = [&](uint32_t t) {
         const int slot = t & 1;
@@ -152,21 +158,21 @@ __global__ void __launch_bounds__(448, 1) conv_rb_kernel(const __grid_constant__
         tc::mbar_wait(&bar_mid_full, t & 1u);
         tc::mbar_wait(&bar_d2_empty[slot], ph ^ 1u);
         tc::tc_fence_after();
-        const uint32_t d2 = tmem_base + (uint32_t)slot * set_stride + 2u * p.NB;
-        uint32_t accumulate = 0;
+        if (tc::elect_one()) {
+          const uint32_t d2 = tmem_base + (uint32_t)slot * set_stride + 2u * p.NB;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+          for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx)
+            for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < ksteps) {
-                tc::umma_f16(d2, mid_desc + (uint64_t)((ky * RB_P + kx) * 8 + k * 2),
-                             w2_desc + (uint64_t)((ky * 3 + kx) * b_tap + k * 2), idesc, accumulate);
-                accumulate = 1;
-              }
-        tc::umma_commit(&bar_mid_empty);        // intermediate buffer free once these MMAs retire
-        tc::umma_commit(&bar_d2_full[slot]);
+              for (int k = 0; k < 4; ++k)
+                if (k < ksteps)
+                  tc::umma_f16(d2, mid_desc + (uint64_t)((ky * RB_P + kx) * 8 + k * 2),
+                               w2_desc + (uint64_t)((ky * 3 + kx) * b_tap + k * 2), idesc, (ky | kx | k) ? 1u : 0u);
+          tc::umma_commit(&bar_mid_empty);        // intermediate buffer free once these MMAs retire
+          tc::umma_commit(&bar_d2_full[slot]);
+        }
+        __syncwarp();
       };
       uint32_t nloc = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++nloc;
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(448, 1) conv_rb_kernel(const __grid_constant__
         conv2(t);
       }
     }
-  } else if (warp < 10) {
+  } else if (warp_u < 10) {
     // ===================== epilogue 1: D1 -> act -> swizzled smem operand =====================
     const int g = (warp - 2) >> 2;       // M-tile of the halo region
     const int q = warp & 3;

@@ -37,7 +37,7 @@ struct TcP {
   int Ho, Wo, kh, kw, pad;
   int nch0, nch1, c0, c1;
   int S, NB, cout, tiles_x, tiles_y, slots, resident;
-  uint32_t a_bytes, w_bytes;
+  uint32_t a_bytes, w_bytes, a_tx;   // a_tx = bytes one A-stage TMA box delivers (<= a_bytes, the slot pitch)
   const uint8_t* wpack;
   const float* bias;
   float pre_slope, post_slope;   // act(v) = v > 0 ? v : v * slope  (none: 1, relu: 0, lrelu: 0.1 / 0.2)
@@ -57,6 +57,8 @@ struct TcP {
   // whole row, so each tcgen05.mma fetches exactly its operand bytes (with 128-byte rows every K-slice pulls the
   // full row: ~110 cycles per MMA at N = 48, measured - profiles/r01_conv_knockout.md)
   int nacc;                               // accumulator buffers in TMEM (3 or 6)
+  int fold;                               // mode 3: the 3 kx taps folded into N = 3 * NB (see conv_tc_kernel MODE 3)
+  int fast;                               // streamlined epilogue (all-16-bit, vector stores, full 16-channel chunks)
   int nmma;                               // MMA-issuing warps in use (1..MAX_MMA), tiles dealt round-robin
   int grp;                                // consecutive stages that share one full/empty barrier pair (1 or S)
   int sw32, nq0, nq1;
@@ -106,6 +108,22 @@ __device__ __forceinline__ void store16(T* p, const float v[16]) {
   }
 }
 
+// packed 16-bit pairs <-> fp32 (one F2FP / two bit ops per pair)
+__device__ __forceinline__ uint32_t pack2(float a, float b, __half) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, __nv_bfloat16) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t v, __half) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
+__device__ __forceinline__ float2 unpack2(uint32_t v, __nv_bfloat16) {
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t pack2(float, float, float) { return 0; }          // never instantiated on the fast path
+__device__ __forceinline__ float2 unpack2(uint32_t, float) { return make_float2(0.f, 0.f); }
+
 // all MMAs of one pipeline stage: KH vertical taps x ksteps (<= 4) K-slices of 16 channels.  Descriptor
 // start addresses advance by +2 (32 bytes) per K-slice and by one tile row block per tap.
 template <int KH>
@@ -151,10 +169,25 @@ __device__ __forceinline__ void issue_taps_box(uint32_t d_tmem, uint64_t ad, uin
   }
 }
 
-// MODE: 0 = 128B-swizzled boxes per (kx, chunk); 1 = single box per (tile, chunk); 2 = 32B-swizzled quads per kx.
+// MODE: 0 = 128B-swizzled boxes per (kx, chunk); 1 = single box per (tile, chunk); 2 = 32B-swizzled quads per kx;
+// 3 = "kx-folded" 3x3: tile = 4 rows x 30 columns computed on a 4 x 32 pixel grid (M = 128, one warp per row).  One MMA
+//     per (ky, 16-channel slice) multiplies the grid by the weights of ALL three kx taps at once (N = 3 * NB, the taps
+//     are adjacent row blocks of the layout-1 weight image), so accumulator column block kx of grid pixel b holds the
+//     tap-kx partial sum of INPUT column b; the epilogue adds the three blocks across lanes (out[j] = D0[j] + D1[j+1]
+//     + D2[j+2], two warp shuffles per value).  9 MMAs per tile instead of 27 and the 4 KB A-operand slice is read
+//     from shared memory once per (ky, slice) instead of three times - the SS-mode MMAs of this kernel are bound by
+//     shared-memory operand bandwidth (~55 cycles per N = 48 MMA measured, 24 by tensor math).
 // One instantiation per mode keeps the (register-critical) epilogue free of the other modes' code.
 #ifdef RV_CONV_EXPERIMENTS
 #define RV_DBG(p, bit) ((p).dbg & (bit))
+// kernel-level marks of CTA 0 (role 7): 0 = entry, 1 = prologue done (barriers, TMEM, bias), 2 = exit
+#define RV_MARK(ev)                                                                                \
+  do {                                                                                             \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {            \
+      long long* _t = p.trace + ((size_t)7 * 1000 + (ev)) * 3;                                     \
+      _t[0] = (ev); _t[1] = 0; _t[2] = clock64();                                                  \
+    }                                                                                              \
+  } while (0)
 // device-side timeline of CTA 0: role r writes (event, tile, clock64) triples into its own region of p.trace
 #define RV_TRACE(role, ev, tile)                                                                   \
   do {                                                                                             \
@@ -165,6 +198,7 @@ __device__ __forceinline__ void issue_taps_box(uint32_t d_tmem, uint64_t ad, uin
   } while (0)
 #else
 #define RV_DBG(p, bit) 0
+#define RV_MARK(ev) do { } while (0)
 #define RV_TRACE(role, ev, tile) do { } while (0)
 #endif
 
@@ -175,7 +209,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[MAX_SLOTS], bar_empty[MAX_SLOTS], bar_w, bar_tfull[MAX_ACC], bar_tempty[MAX_ACC];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float bias_s[256];
+  __shared__ __align__(16) float bias_s[256];
 
   const uint32_t raw = tc::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -191,6 +225,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   // Programmatic dependent launch: let the next kernel of the stream start its own prologue as soon as SMs free
   // up; everything below that reads or writes activations sits behind griddepcontrol.wait, while barrier init,
   // TMEM allocation, bias and the (constant) weight fetch overlap the previous kernel's tail.
+  RV_MARK(0);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (threadIdx.x == 0) {
@@ -216,11 +251,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  RV_MARK(1);
 
   // Register re-balancing (512 threads x 128 registers at launch): the four single-thread role warps (warpgroup 0)
   // hand registers to the three epilogue warpgroups, whose 16-column drain + prefetch loop otherwise spills.
-  if (warp_u < 1 + MAX_MMA) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;" ::: "memory");
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 144;" ::: "memory");
+  if (warp_u < 1 + MAX_MMA) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 152;" ::: "memory");
 
   if (warp_u == 0) {
     // ============================ TMA producer ============================
@@ -234,7 +270,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       }
       __syncwarp();
       asm volatile("griddepcontrol.wait;" ::: "memory");   // activations of the previous kernel are now visible
-      const uint32_t tx_bytes = p.a_bytes + (p.resident ? 0u : p.w_bytes);
+      const uint32_t tx_bytes = p.a_tx + (p.resident ? 0u : p.w_bytes);
       int slot = 0;
       uint32_t ph = 0;
       int tr_n = 0; (void)tr_n;
@@ -274,7 +310,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           __syncwarp();
           // stage order: mode 0 = (kx, chunk), mode 1 = (chunk), mode 2 = (kx)
           if (MODE == 2) ++kx;
-          else if (++ch == nchunks) { ch = 0; kx += (MODE == 1) ? 0 : 1; }
+          else if (++ch == nchunks) { ch = 0; kx += (MODE == 1 || MODE == 3) ? 0 : 1; }
           if (++sub == p.grp) {
             sub = 0;
             if (++slot == p.slots) { slot = 0; ph ^= 1u; }
@@ -294,11 +330,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     const int id = warp_u - 1;
     // warp-uniform control flow: all 32 lanes run the loop, an elected lane issues (see tc::umma_f16_elect)
     if (id < p.nmma) {
-      const uint32_t idesc = tc::umma_idesc(p.fmt, 128, p.NB);
+      const uint32_t idesc = tc::umma_idesc(p.fmt, 128, (MODE == 3) ? 3 * p.NB : p.NB);
       // SBO (bits [32,46)): 1024 B between 8-row groups in mode 0, bw*128 B (next tile row) in mode 1
       const uint64_t adesc0 = (MODE == 2) ? tc::umma_desc_sw32(tc::smem_u32(smemA))
                                           : tc::umma_desc_sw128(tc::smem_u32(smemA)) +
                                                 ((MODE == 1) ? ((uint64_t)((p.bw * 128 - 1024) >> 4) << 32) : 0ull);
+      // (mode 3: the 4 x 32 grid rows are contiguous in the box, 8-row groups 1024 B apart like mode 0)
       const uint64_t bdesc0 = (MODE == 2) ? tc::umma_desc_sw32(tc::smem_u32(smemW)) : tc::umma_desc_sw128(tc::smem_u32(smemW));
       const uint32_t a_step = p.a_bytes >> 4, w_step = p.w_bytes >> 4, b_tap = (uint32_t)(p.NB * 128) >> 4;
       const uint32_t ngrp = (uint32_t)(p.S / p.grp);   // barrier groups (smem slots) per tile: 1 or S
@@ -338,6 +375,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                 tc::umma_f16(d_tmem, ad + (uint64_t)(qd * q_step + ky * (TW * 32 / 16)), bd + (uint64_t)((ky * nq + qd) * bq),
                              idesc, (s | ky | qd) ? 1u : 0u);
               }
+          } else if constexpr (MODE == 3) {
+            // stage = channel chunk; A view for tap row ky starts ky grid rows (32 pixels = 4096 B) into the box
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < ksteps)
+                  tc::umma_f16(d_tmem, ad + (uint64_t)(ky * 256 + k * 2), bd + (uint64_t)(ky * 3 * b_tap + k * 2), idesc,
+                               (s | ky | k) ? 1u : 0u);
           } else if constexpr (MODE == 1) {
             switch (p.kh) {
               case 1: issue_taps_box<1>(d_tmem, ad, bd, idesc, ksteps, b_tap, p.bw, p.bo_force, s ? 1u : 0u); break;
@@ -387,7 +433,264 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     // group g drains local tiles t = g, g + 3, g + 6, ...; tile t lives in accumulator t % nacc
     uint32_t tl = (uint32_t)grp;
     int tr_n = (q == 0 && lane == 0) ? 0 : 1000000; (void)tr_n;
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += NACC * gridDim.x, tl += NACC) {
+    if constexpr (MODE == 3 && sizeof(TI) == 2 && sizeof(TR) == 2 && sizeof(TO) == 2) {
+      // ---- kx-folded tile: warp q = grid row, lane = grid column b (input column tile_x0 - pad + b) ----
+      const int nch = p.NB >> 4;
+      const int act_pre = (pre_slope == 1.f) ? 0 : (pre_slope == 0.f ? 1 : 2);
+      const int act_post = (post_slope == 1.f) ? 0 : (post_slope == 0.f ? 1 : 2);
+      // Residual vectors are fetched ONE TILE AHEAD: once the epilogue (not the MMAs) paces the kernel the accumulator
+      // is already complete when a group comes back for its next tile, so a prefetch issued just before the tfull wait
+      // hides nothing and the L2 / HBM latency of the 96-byte-strided loads lands on the critical path.
+      const int nbase = nblk * p.NB;
+      auto tile_pixel = [&](int tile, bool& valid) -> size_t {
+        const int oy = (tile / p.tiles_x) * p.th + q, ox = (tile % p.tiles_x) * p.tw + lane;
+        valid = (tile < ntiles) && (lane < p.tw) && (oy < p.Ho) && (ox < p.Wo);
+        return valid ? (size_t)oy * p.Wo + ox : 0;
+      };
+      uint4 rp[3][2], rn[3][2];
+      auto fetch_res = [&](size_t pix, uint4 (&dst)[3][2]) {
+        if (res != nullptr) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (c < nch) {
+              const uint4* q4 = reinterpret_cast<const uint4*>(res + pix * p.res_cs + nbase + c * 16);
+              dst[c][0] = __ldg(q4);
+              dst[c][1] = __ldg(q4 + 1);
+            }
+        }
+      };
+      {
+        bool v0;
+        const size_t p0 = tile_pixel(blockIdx.x + grp * gridDim.x, v0);
+        fetch_res(p0, rn);
+      }
+      for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += NACC * gridDim.x, tl += NACC) {
+        const uint32_t acc = tl % (uint32_t)p.nacc, accph = (tl / (uint32_t)p.nacc) & 1u;
+        bool valid, valid_next;
+        const size_t pix = tile_pixel(tile, valid);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { rp[c][0] = rn[c][0]; rp[c][1] = rn[c][1]; }
+        const size_t pix_next = tile_pixel(tile + NACC * gridDim.x, valid_next);
+        fetch_res(pix_next, rn);
+        RV_TRACE(2 + grp, 0, tile);
+        tc::mbar_wait(&bar_tfull[acc], accph);
+        tc::tc_fence_after();
+        RV_TRACE(2 + grp, 1, tile);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {          // 3 * NB <= 256 -> at most 5 chunks; unrolled so rp[] stays in registers
+          if (c >= nch) break;
+          const int n0 = c * 16;
+          uint32_t d0[16], d1[16], d2[16];
+          tc::tmem_ld16(taddr + (uint32_t)n0, d0);
+          tc::tmem_ld16(taddr + (uint32_t)(p.NB + n0), d1);
+          tc::tmem_ld16(taddr + (uint32_t)(2 * p.NB + n0), d2);
+          tc::tmem_ld_wait();
+          if (c + 1 == nch) {
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bar_tempty[acc]);
+          }
+          RV_TRACE(2 + grp, 2, tile);
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float s1 = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[j]), 1);
+            const float s2 = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[j]), 2);
+            v[j] = (__uint_as_float(d0[j]) + s1) + (s2 + bias_s[n0 + j]);
+          }
+          if (act_pre == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (act_pre == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * pre_slope);
+          }
+          if (gate != nullptr) {
+            const uint4* g4 = reinterpret_cast<const uint4*>(gate + pix * p.gate_cs + nbase + n0);
+            const uint4 ga = __ldg(g4), gb = __ldg(g4 + 1);
+            const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 g2 = unpack2(gw[j], TI());
+              v[2 * j] *= g2.x;
+              v[2 * j + 1] *= g2.y;
+            }
+          }
+          if (res != nullptr) {
+            uint4 ra, rb;
+            if (c < 3) { ra = rp[c < 3 ? c : 0][0]; rb = rp[c < 3 ? c : 0][1]; }
+            else {
+              const uint4* q4 = reinterpret_cast<const uint4*>(res + pix * p.res_cs + nbase + n0);
+              ra = __ldg(q4); rb = __ldg(q4 + 1);
+            }
+            const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 r2 = unpack2(rw[j], TR());
+              v[2 * j] += r2.x;
+              v[2 * j + 1] += r2.y;
+            }
+          }
+          if (act_post == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (act_post == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * post_slope);
+          }
+          if (p.post_clamp3) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], -3.f), 3.f);
+          }
+          if (valid) {
+            uint4 o0, o1;
+            o0.x = pack2(v[0], v[1], TO()); o0.y = pack2(v[2], v[3], TO()); o0.z = pack2(v[4], v[5], TO()); o0.w = pack2(v[6], v[7], TO());
+            o1.x = pack2(v[8], v[9], TO()); o1.y = pack2(v[10], v[11], TO()); o1.z = pack2(v[12], v[13], TO()); o1.w = pack2(v[14], v[15], TO());
+            uint4* o = reinterpret_cast<uint4*>(out + pix * p.out_cs + nbase + n0);
+            o[0] = o0;
+            o[1] = o1;
+          }
+        }
+        RV_TRACE(2 + grp, 3, tile);
+      }
+      tl = 0x7fffffffu;
+    } else if constexpr (sizeof(TI) == 2 && sizeof(TR) == 2 && sizeof(TO) == 2) {
+      if (p.fast) {
+        // ---- fast path: 16-bit in / residual / out, NB = 16 * nch full chunks, 32-byte vector accesses ----
+        // The generic loop below costs ~450 SASS instructions per 16-column chunk (runtime layout / tail handling);
+        // with only 3 epilogue warps per scheduler that made the EPILOGUE the pacing stage once the MMA issue was
+        // fixed (profiles/r01_conv_timeline.md).  Here: all TMEM loads of a tile in flight at once, packed
+        // conversions, uniform branches hoisted out of the per-value loops.
+        const int nch = p.NB >> 4;
+        const int act_pre = (pre_slope == 1.f) ? 0 : (pre_slope == 0.f ? 1 : 2);
+        const int act_post = (post_slope == 1.f) ? 0 : (post_slope == 0.f ? 1 : 2);
+        // residual vectors are fetched one tile ahead (see the MODE 3 branch above)
+        const int nbase = nblk * p.NB;
+        auto tile_pixel = [&](int tile, bool& valid) -> size_t {
+          const int oy = (tile / p.tiles_x) * p.th + ty, ox = (tile % p.tiles_x) * p.tw + tx;
+          valid = (tile < ntiles) && (oy < p.Ho) && (ox < p.Wo);
+          return valid ? (size_t)oy * p.Wo + ox : 0;          // out-of-image lanes read pixel 0, never store
+        };
+        uint4 rp[3][2], rn[3][2];
+        auto fetch_res = [&](size_t pix, uint4 (&dst)[3][2]) {
+          if (RV_DBG(p, 128)) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dst[c][0] = dst[c][1] = make_uint4(0, 0, 0, 0);
+          } else if (res != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              if (c < nch) {
+                const uint4* q4 = reinterpret_cast<const uint4*>(res + pix * p.res_cs + nbase + c * 16);
+                dst[c][0] = __ldg(q4);
+                dst[c][1] = __ldg(q4 + 1);
+              }
+          }
+        };
+        {
+          bool v0;
+          const size_t p0 = tile_pixel(blockIdx.x + grp * gridDim.x, v0);
+          fetch_res(p0, rn);
+        }
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += NACC * gridDim.x, tl += NACC) {
+          const uint32_t acc = tl % (uint32_t)p.nacc, accph = (tl / (uint32_t)p.nacc) & 1u;
+          bool valid, valid_next;
+          const size_t pix = tile_pixel(tile, valid);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { rp[c][0] = rn[c][0]; rp[c][1] = rn[c][1]; }
+          const size_t pix_next = tile_pixel(tile + NACC * gridDim.x, valid_next);
+          fetch_res(pix_next, rn);
+          RV_TRACE(2 + grp, 0, tile);
+          tc::mbar_wait(&bar_tfull[acc], accph);
+          tc::tc_fence_after();
+          RV_TRACE(2 + grp, 1, tile);
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride;
+          for (int c3 = 0; c3 < nch; c3 += 3) {
+            uint32_t r[3][16];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              if (c3 + c < nch) tc::tmem_ld16(taddr + (uint32_t)(c3 + c) * 16, r[c]);
+            tc::tmem_ld_wait();
+            if (c3 + 3 >= nch) {
+              // accumulator fully in registers: hand it back to the MMA warps before the arithmetic and the stores
+              tc::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) tc::mbar_arrive(&bar_tempty[acc]);
+            }
+            RV_TRACE(2 + grp, 2, tile);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              if (c3 + c >= nch) break;
+              const int n0 = (c3 + c) * 16;
+              float v[16];
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = RV_DBG(p, 32) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(&bias_s[n0 + j]);
+                v[j] = __uint_as_float(r[c][j]) + b4.x;
+                v[j + 1] = __uint_as_float(r[c][j + 1]) + b4.y;
+                v[j + 2] = __uint_as_float(r[c][j + 2]) + b4.z;
+                v[j + 3] = __uint_as_float(r[c][j + 3]) + b4.w;
+              }
+              if (act_pre == 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+              } else if (act_pre == 2) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * pre_slope);
+              }
+              if (gate != nullptr) {
+                const uint4* g4 = reinterpret_cast<const uint4*>(gate + pix * p.gate_cs + nbase + n0);
+                const uint4 ga = __ldg(g4), gb = __ldg(g4 + 1);
+                const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 g2 = unpack2(gw[j], TI());
+                  v[2 * j] *= g2.x;
+                  v[2 * j + 1] *= g2.y;
+                }
+              }
+              if (res != nullptr) {
+                uint4 ra, rb;
+                if (c3 == 0) { ra = rp[c][0]; rb = rp[c][1]; }
+                else {
+                  const uint4* q4 = reinterpret_cast<const uint4*>(res + pix * p.res_cs + nbase + n0);
+                  ra = __ldg(q4); rb = __ldg(q4 + 1);
+                }
+                const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 r2 = unpack2(rw[j], TR());
+                  v[2 * j] += r2.x;
+                  v[2 * j + 1] += r2.y;
+                }
+              }
+              if (act_post == 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+              } else if (act_post == 2) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * post_slope);
+              }
+              if (p.post_clamp3) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], -3.f), 3.f);
+              }
+              if (valid && !RV_DBG(p, 64)) {
+                uint4 o0, o1;
+                o0.x = pack2(v[0], v[1], TO()); o0.y = pack2(v[2], v[3], TO()); o0.z = pack2(v[4], v[5], TO()); o0.w = pack2(v[6], v[7], TO());
+                o1.x = pack2(v[8], v[9], TO()); o1.y = pack2(v[10], v[11], TO()); o1.z = pack2(v[12], v[13], TO()); o1.w = pack2(v[14], v[15], TO());
+                uint4* o = reinterpret_cast<uint4*>(out + pix * p.out_cs + nbase + n0);
+                o[0] = o0;
+                o[1] = o1;
+              }
+            }
+          }
+          RV_TRACE(2 + grp, 3, tile);
+        }
+        tl = 0x7fffffffu;   // generic loop below is skipped
+      }
+    }
+    for (int tile = (tl == 0x7fffffffu) ? ntiles : blockIdx.x + grp * gridDim.x; tile < ntiles; tile += NACC * gridDim.x, tl += NACC) {
       const uint32_t acc = tl % (uint32_t)p.nacc, accph = (tl / (uint32_t)p.nacc) & 1u;
       const int oy = (tile / p.tiles_x) * p.th + ty, ox = (tile % p.tiles_x) * p.tw + tx;
       const bool valid = (oy < p.Ho) && (ox < p.Wo);
@@ -506,6 +809,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1 + MAX_MMA) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  RV_MARK(2);
 }
 
 PFN_tmapEncodeTiled get_tmap_encoder() {
@@ -568,6 +872,7 @@ static int launch_tc_mode(const CUtensorMap& tm0, const CUtensorMap& tm1, const 
 template <typename TI, typename TR, typename TO>
 static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& p, dim3 grid, size_t smem, cudaStream_t st) {
   if (p.sw32) return launch_tc_mode<TI, TR, TO, 2>(tm0, tm1, p, grid, smem, st);
+  if (p.fold) return launch_tc_mode<TI, TR, TO, 3>(tm0, tm1, p, grid, smem, st);
   if (p.single_box) return launch_tc_mode<TI, TR, TO, 1>(tm0, tm1, p, grid, smem, st);
   return launch_tc_mode<TI, TR, TO, 0>(tm0, tm1, p, grid, smem, st);
 }
@@ -597,17 +902,43 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   p.NB = d->nb; p.cout = d->cout;
   const int nblk = (d->cout + p.NB - 1) / p.NB;
   const size_t budget = (size_t)g_max_smem - 1024 /*alignment*/ - 4096 /*static: barriers, bias*/;
+  { const char* e = getenv("REFVSR_BO_FORCE"); p.bo_force = e ? atoi(e) : -1; }
+  { const char* e = getenv("REFVSR_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("REFVSR_CONV_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+  const int rdt = d->res ? d->res_dtype : d->out_dtype;
+  auto al16 = [](const void* q, int cs, int dt) { return q == nullptr || (((uintptr_t)q % 16 == 0) && ((cs * dtype_size(dt)) % 16 == 0)); };
+  p.vec_ok = al16(d->out, d->out_cs, d->out_dtype) && al16(d->gate, d->gate_cs, d->in_dtype) && al16(d->res, d->res_cs, rdt);
+  static const bool fast_ok = getenv("REFVSR_NO_FAST_EPILOGUE") == nullptr;
+  p.fast = fast_ok && p.vec_ok && !d->pixel_shuffle && (d->cout % p.NB == 0) && d->out_dtype != RV_F32 && rdt != RV_F32 &&
+           d->out_dtype == d->in_dtype && rdt == d->in_dtype && (p.dbg & 31) == 0;   // knock-out bits 32/64/128 are fast-path experiments
   // mode 1 (single box per tile and chunk) when the whole weight set stays resident next to >= 2 boxes
-  p.single_box = 0; p.sw32 = 0; p.nq0 = p.nq1 = 0; p.q_bytes = 0;
-  if (d->layout == 1) {
+  p.single_box = 0; p.sw32 = 0; p.nq0 = p.nq1 = 0; p.q_bytes = 0; p.fold = 0;
+  if (d->layout == 1 || d->layout == 3) {
     RV_REQUIRE(d->kh == d->kw && (d->kh == 1 || d->kh == 3 || d->kh == 5 || d->kh == 7), "rv_conv2d(tc): layout 1 needs a square 1/3/5/7 kernel");
     p.single_box = 1;
+    // mode 3 (kx-folded N = 3 * NB) shares the layout-1 weight image; it needs the streamlined 16-bit epilogue
+    static const bool fold_ok = getenv("REFVSR_NO_KXFOLD") == nullptr;
+    const size_t w_fold = (size_t)(p.nch0 + p.nch1) * 9 * p.NB * 128;
+    // measured (profiles/r01_conv_timeline.md): folding wins where the MMA phase dominates - two 64-channel chunks or
+    // narrow outputs (NB <= 32, where N = NB under-uses each A-operand read most) - and loses on the single-chunk
+    // 48 -> 48 convs, whose epilogue (heavier when folded: 3x TMEM reads + shuffles) already paces the kernel
+    static const bool fold_all = getenv("REFVSR_KXFOLD_ALL") != nullptr;
+    const bool fold_pays = fold_all || (p.nch0 + p.nch1) >= 2 || p.NB <= 32;
+    p.fold = fold_ok && fold_pays && d->layout == 1 && d->kh == 3 && p.fast && p.dbg == 0 && 9 * p.NB <= 512 /* three N = 3 * NB accumulators in TMEM */ && w_fold + 3 * (size_t)(6 * 32 * 128) <= budget;
   }
-  if (p.single_box) {
-    p.th = 16; p.tw = 8; p.tw_shift = 3;
-    p.bw = (d->kw == 1) ? 8 : 16;
+  if (p.fold) {
+    p.th = 4; p.tw = 30; p.tw_shift = 0;
+    p.bw = 32;                           // the 4 x 32 pixel grid of a tile: input columns tile_x0 - pad .. + 31
     p.S = p.nch0 + p.nch1;
-    p.a_bytes = (uint32_t)(p.th + d->kh - 1) * p.bw * 128;
+    p.a_tx = (uint32_t)(p.th + d->kh - 1) * p.bw * 128;
+    p.a_bytes = p.a_tx;
+    p.w_bytes = (uint32_t)d->kh * d->kw * p.NB * 128;
+  } else if (p.single_box) {
+    p.th = 16; p.tw = 8; p.tw_shift = 3;
+    p.bw = p.tw + d->kw - 1;            // box = tile + halo; rows of the box are bw pixels (bw * 128 B) apart
+    p.S = p.nch0 + p.nch1;
+    p.a_tx = (uint32_t)(p.th + d->kh - 1) * p.bw * 128;
+    p.a_bytes = (p.a_tx + 1023u) & ~1023u;   // slots stay 1024-byte aligned (swizzle atom)
     p.w_bytes = (uint32_t)d->kh * d->kw * p.NB * 128;
     RV_REQUIRE((size_t)p.S * p.w_bytes + 2 * (size_t)p.a_bytes <= budget, "rv_conv2d(tc): layout 1 weights do not fit in shared memory");
   } else if (d->layout == 2) {
@@ -617,16 +948,15 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
     p.S = d->kw;
     p.q_bytes = (uint32_t)(TH + d->kh - 1) * TW * 32;
     p.a_bytes = (uint32_t)(p.nq0 + p.nq1) * p.q_bytes;
+    p.a_tx = p.a_bytes;
     p.w_bytes = (uint32_t)d->kh * (p.nq0 + p.nq1) * p.NB * 32;
   } else {
     p.th = TH; p.tw = TW; p.tw_shift = 4; p.bw = TW;
     p.S = d->kw * (p.nch0 + p.nch1);
     p.a_bytes = (uint32_t)(TH + d->kh - 1) * TW * 128;
+    p.a_tx = p.a_bytes;
     p.w_bytes = (uint32_t)d->kh * p.NB * 128;
   }
-  { const char* e = getenv("REFVSR_BO_FORCE"); p.bo_force = e ? atoi(e) : -1; }
-  { const char* e = getenv("REFVSR_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
-  { const char* e = getenv("REFVSR_CONV_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
   p.tiles_x = (p.Wo + p.tw - 1) / p.tw; p.tiles_y = (p.Ho + p.th - 1) / p.th;
   // shared-memory plan: weights resident when they leave room for >= 3 A slots
   const size_t w_all = (size_t)p.S * p.w_bytes;
@@ -657,18 +987,16 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   p.gate = d->gate; p.gate_cs = d->gate_cs; p.res = d->res; p.res_cs = d->res_cs;
   p.out = d->out; p.out_cs = d->out_cs; p.pixel_shuffle = d->pixel_shuffle;
   p.fmt = d->in_dtype == RV_BF16 ? 1 : 0;
-  const int rdt = d->res ? d->res_dtype : d->out_dtype;
-  auto al16 = [](const void* q, int cs, int dt) { return q == nullptr || (((uintptr_t)q % 16 == 0) && ((cs * dtype_size(dt)) % 16 == 0)); };
-  p.vec_ok = al16(d->out, d->out_cs, d->out_dtype) && al16(d->gate, d->gate_cs, d->in_dtype) && al16(d->res, d->res_cs, rdt);
-  p.acc_stride = (uint32_t)p.NB;
+  p.acc_stride = (uint32_t)(p.fold ? 3 * p.NB : p.NB);
   uint32_t cols = 32;
-  p.nacc = (6 * p.NB <= 512) ? 6 : 3;
+  // accumulator t % nacc must always belong to the same epilogue group (t % 3): nacc is 3 or 6
+  p.nacc = (6 * p.acc_stride <= 512) ? 6 : 3;
   // issuers: as many as there are whole tiles in flight in shared memory (and accumulators to write to)
   static const int nmma_env = getenv("REFVSR_NMMA") ? atoi(getenv("REFVSR_NMMA")) : 0;
   // (an issuer further ahead than the shared-memory ring would alias mbarrier phases, so this is a hard limit)
   p.nmma = std::max(1, std::min(std::min((int)MAX_MMA, p.slots * p.grp / p.S), p.nacc));
   if (nmma_env > 0) p.nmma = std::min(p.nmma, nmma_env);
-  while (cols < (uint32_t)p.nacc * p.NB) cols <<= 1;
+  while (cols < (uint32_t)p.nacc * p.acc_stride) cols <<= 1;
   p.tmem_cols = cols;
 
   CUtensorMap tm0, tm1;

@@ -105,6 +105,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + (size_t)p.nk * A_CH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // provably warp-uniform copy for the role dispatch
   const int m0 = blockIdx.x * MT_BM;
 
   if (threadIdx.x == 0) {
@@ -121,47 +122,50 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  // Producer and MMA warps run warp-uniform control flow with one elected lane issuing (tc::elect_one): the compiler
+  // then keeps descriptors / barrier addresses in uniform registers instead of a per-instruction broadcast waterfall.
+  if (warp_u == 0) {
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(&bar_a, (uint32_t)p.nk * A_CH);
       for (int c = 0; c < p.nk; ++c) tc::tma_load_2d(&tmA, &bar_a, smemA + (size_t)c * A_CH, c * 64, m0);
-      uint32_t it = 0;
-      for (int nt = 0; nt < p.ntiles_n; ++nt)
-        for (int c = 0; c < p.nk; ++c, ++it) {
-          const int slot = it % p.slots;
-          const uint32_t ph = (it / p.slots) & 1u;
-          tc::mbar_wait(&bar_empty[slot], ph ^ 1u);
+    }
+    __syncwarp();
+    int slot = 0;
+    uint32_t ph = 0;
+    for (int nt = 0; nt < p.ntiles_n; ++nt)
+      for (int c = 0; c < p.nk; ++c) {
+        tc::mbar_wait(&bar_empty[slot], ph ^ 1u);
+        if (tc::elect_one()) {
           tc::mbar_expect_tx(&bar_full[slot], B_ST);
           tc::tma_load_2d(&tmB, &bar_full[slot], smemB + (size_t)slot * B_ST, c * 64, nt * MT_BN);
         }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = tc::umma_idesc(0, MT_BM, MT_BN);
-      tc::mbar_wait(&bar_a, 0);
-      uint32_t it = 0;
-      for (int nt = 0; nt < p.ntiles_n; ++nt) {
-        const uint32_t acc = nt & 1u, accph = (nt >> 1) & 1u;
-        tc::mbar_wait(&bar_tempty[acc], accph ^ 1u);
+        __syncwarp();
+        if (++slot == p.slots) { slot = 0; ph ^= 1u; }
+      }
+  } else if (warp_u == 1) {
+    const uint32_t idesc = tc::umma_idesc(0, MT_BM, MT_BN);
+    const uint64_t adesc0 = tc::umma_desc_sw128(tc::smem_u32(smemA)), bdesc0 = tc::umma_desc_sw128(tc::smem_u32(smemB));
+    tc::mbar_wait(&bar_a, 0);
+    int slot = 0;
+    uint32_t ph = 0;
+    for (int nt = 0; nt < p.ntiles_n; ++nt) {
+      const uint32_t acc = nt & 1u, accph = (nt >> 1) & 1u;
+      tc::mbar_wait(&bar_tempty[acc], accph ^ 1u);
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * MT_BN;
+      for (int c = 0; c < p.nk; ++c) {
+        tc::mbar_wait(&bar_full[slot], ph);
         tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * MT_BN;
-        uint32_t accumulate = 0;
-        for (int c = 0; c < p.nk; ++c, ++it) {
-          const int slot = it % p.slots;
-          const uint32_t ph = (it / p.slots) & 1u;
-          tc::mbar_wait(&bar_full[slot], ph);
-          tc::tc_fence_after();
-          const uint32_t a0 = tc::smem_u32(smemA + (size_t)c * A_CH);
-          const uint32_t b0 = tc::smem_u32(smemB + (size_t)slot * B_ST);
+        if (tc::elect_one()) {
+          const uint64_t ad = adesc0 + (uint64_t)((uint32_t)c * (A_CH >> 4));
+          const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)slot * (B_ST >> 4));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            tc::umma_f16(d_tmem, tc::umma_desc_sw128(a0 + k * 32), tc::umma_desc_sw128(b0 + k * 32),
-                         idesc, accumulate);
-            accumulate = 1;
-          }
+          for (int k = 0; k < 4; ++k) tc::umma_f16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (c | k) ? 1u : 0u);
           tc::umma_commit(&bar_empty[slot]);
+          if (c + 1 == p.nk) tc::umma_commit(&bar_tfull[acc]);
         }
-        tc::umma_commit(&bar_tfull[acc]);
+        __syncwarp();
+        if (++slot == p.slots) { slot = 0; ph ^= 1u; }
       }
     }
   } else {
@@ -181,10 +185,23 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc::tmem_ld32(taddr + c0, r);
         tc::tmem_ld_wait();
         if (c0 + 32 <= nvalid) {
+          // chunk maximum first (a tree of independent FMNMX), index search only when it beats the running best:
+          // a serial `if (v > best)` scan is one dependent compare-select chain per element and made this loop,
+          // not the MMAs, the pacing stage in single-pass mode.  Same result: strict > keeps the earliest maximum
+          // across chunks, the search below takes the first position inside the chunk.
+          float m8[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = __uint_as_float(r[j]);
-            if (v > best) { best = v; bidx = rbase + c0 + j; }
+          for (int j = 0; j < 8; ++j)
+            m8[j] = fmaxf(fmaxf(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])),
+                          fmaxf(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+          const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+          if (mx > best) {
+            best = mx;
+            int jj = 31;
+#pragma unroll
+            for (int j = 30; j >= 0; --j)
+              if (__uint_as_float(r[j]) == mx) jj = j;
+            bidx = rbase + c0 + jj;
           }
         } else {
 #pragma unroll

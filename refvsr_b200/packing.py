@@ -144,7 +144,7 @@ def pack_tc(weight, srcs, dtype, nb, layout=0):
     wc = torch.stack(chunks, 0)                               # (nchunks, cout, 64, kh, kw)
     wpad = w.new_zeros(nchunks, nblk * nb, 64, kh, kw)
     wpad[:, :cout] = wc
-    if layout == 1:   # [nblk][chunk][ky][kx][n][c]: one stage per chunk holding all kh*kw taps
+    if layout in (1, 3):   # [nblk][chunk][ky][kx][n][c]: one stage per chunk holding all kh*kw taps (3 = same image, no kx-fold)
         S, kh_eff = nchunks, kh * kw
         t = wpad.view(nchunks, nblk, nb, 64, kh, kw).permute(1, 0, 4, 5, 2, 3).contiguous()
     else:             # [nblk][kx][chunk][ky][n][c]
@@ -158,29 +158,31 @@ def pack_tc(weight, srcs, dtype, nb, layout=0):
     return out.view(nblk, S, kh_eff, nb, 64).to(dtype).contiguous()
 
 
-DEFAULT_TC_LAYOUT = 0                    # 0: 128B-swizzled 64-channel boxes, 2: 32B-swizzled 16-channel quads
+DEFAULT_TC_LAYOUT = 1                    # 1: one box per tile (falls back to 0 when the taps do not fit), 0: boxes per (kx, chunk),
+                                         # 2: 32B-swizzled 16-channel quads
 SMEM_BUDGET = 232448 - 1024 - 4096      # opt-in shared memory per CTA minus alignment and static (conv_tc.cu)
 
 
 def layout1_fits(kh, kw, srcs, nb):
-    """layout 1 needs all taps of all chunks resident in shared memory next to >= 3 activation boxes"""
+    """layout 1 needs all taps of all chunks resident in shared memory next to >= 3 activation boxes
+    (box = (16 + kh - 1) rows x (8 + kw - 1) pixels x 128 B, slot pitch rounded up to 1024 B - conv_tc.cu)"""
     if kh != kw or kh not in (1, 3, 5, 7):
         return False
     nchunks = sum((a + 63) // 64 for _, a in srcs)
     w_all = nchunks * kh * kw * nb * 128
-    a_bytes = (16 + kh - 1) * (8 if kw == 1 else 16) * 128
+    a_bytes = ((16 + kh - 1) * (8 + kw - 1) * 128 + 1023) // 1024 * 1024
     return w_all + 3 * a_bytes <= SMEM_BUDGET
 
 
 def choose_layout(kh, kw, srcs, nb):
-    """Default: layout 0 (one TMA box per (kx, chunk) stage).  Layout 1 (one box per tile and chunk, the kh x kw
-    taps as shifted UMMA descriptor views of it) is numerically identical and moves 1.7x fewer bytes from L2, but
-    measured SLOWER end to end on B200 (36.1 vs 30.3 ms / window, profiles/r01_conv_sweep.md), so it is opt-in:
-    REFVSR_TC_LAYOUT=1."""
+    """Default: layout 1 (ONE TMA box per tile and channel chunk; the kh x kw taps are shifted UMMA descriptor views
+    of it) whenever all taps stay resident in shared memory, else layout 0 (one box per (kx, chunk) stage).  Layout 1
+    moves 1.7x fewer bytes from L2 and keeps >= 3 whole tiles in flight, which the multi-issuer MMA path needs
+    (profiles/r01_conv_timeline.md: 13.5 vs 16.2 ms / window).  REFVSR_TC_LAYOUT=0|1|2 forces a layout."""
     import os
     forced = int(os.environ.get('REFVSR_TC_LAYOUT', str(DEFAULT_TC_LAYOUT)))
-    if forced == 1:
-        return 1 if layout1_fits(kh, kw, srcs, nb) else 0
+    if forced in (1, 3):     # 3 = layout-1 weight image with the kx-folded 3x3 mode disabled (A/B measurements)
+        return forced if layout1_fits(kh, kw, srcs, nb) else 0
     return forced
 
 

@@ -94,13 +94,14 @@ def test_conv_simt(cuda_ops, oracle_ops, case, prec):
 
 @pytest.mark.parametrize('case', [c for c in CONV_CASES if c[6] == 1], ids=[c[0] for c in CONV_CASES if c[6] == 1])
 @pytest.mark.parametrize('prec', ['fp16', 'bf16'])
-@pytest.mark.parametrize('layout', [0, 1, 2])
+@pytest.mark.parametrize('layout', [0, 1, 2, 3])
 def test_conv_tc(cuda_ops, oracle_ops, case, prec, layout):
     """layout 0: one 128B-swizzled 64-channel TMA box per (kx, chunk) stage; layout 1: one box per (tile, chunk), taps
     as shifted UMMA descriptor views (only where all taps stay resident in shared memory); layout 2: 32B-swizzled
     16-channel quads (one UMMA_K slice per row)"""
-    if layout == 1 and not packing.layout1_fits(case[5], case[5], case[3], packing.choose_nb(case[4])):
+    if layout in (1, 3) and not packing.layout1_fits(case[5], case[5], case[3], packing.choose_nb(case[4])):
         pytest.skip('weights of this conv are streamed (layout 0 only)')
+    # layout 3 = the layout-1 weight image with the kx-folded 3x3 mode disabled (layout 1 folds when eligible)
     lc, out, exp = _run_conv(cuda_ops, oracle_ops, case, DT[prec], prefer_tc=True, tc_layout=layout)
     assert lc.impl == IMPL_TC and lc.layout == layout, 'stride-1 16-bit convs must take the tcgen05 path'
     close(out, exp, TOL[out.dtype] if out.dtype != torch.float32 else 2e-4, f'conv_tc[{case[0]},{prec}]')

@@ -17,13 +17,14 @@ ops = L.CudaOps()
 from refvsr_b200 import packing
 from refvsr_b200.lib import ACT_RELU
 H, W, C = (int(sys.argv[1]), int(sys.argv[2]), 48) if len(sys.argv) > 2 else (540, 960, 48)
+print('geometry', H, W, C, 'layout', os.environ.get('REFVSR_TC_LAYOUT'), 'nmma', os.environ.get('REFVSR_NMMA'))
 dt = torch.bfloat16
 wgt = torch.randn(C, C, 3, 3) * 0.05
 layer = packing.pack_conv('x', wgt, torch.zeros(C), [(C, C)], 1, 1, dt, 'cuda', True)
 x = torch.randn((H, W, C), device='cuda').to(dt)
 r = torch.randn((H, W, C), device='cuda').to(dt)
 y = torch.empty((H, W, C), device='cuda', dtype=dt)
-trace = torch.zeros((5, 1000, 3), dtype=torch.int64, device='cuda')
+trace = torch.zeros((8, 1000, 3), dtype=torch.int64, device='cuda')
 for i in range(3):
     ops.conv2d(layer, x, None, y, res=r, act_pre=ACT_RELU)
 torch.cuda.synchronize()
@@ -33,13 +34,13 @@ torch.cuda.synchronize()
 del os.environ['REFVSR_CONV_TRACE']
 t = trace.cpu()
 t0 = int(t[:, :, 2][t[:, :, 2] > 0].min())
-names = {0: 'producer', 1: 'mma', 2: 'epi0', 3: 'epi1', 4: 'epi2'}
-for role in range(5):
+names = {0: 'producer', 1: 'mma0', 2: 'epi0', 3: 'epi1', 4: 'epi2', 5: 'mma1', 6: 'mma2', 7: 'kernel marks (entry, prologue done, exit)'}
+for role in range(8):
     ev = [(int(e), int(tile), int(c) - t0) for e, tile, c in t[role].tolist() if c > 0]
     print(f'== {names[role]}: {len(ev)} events; first {ev[0][2] if ev else None} last {ev[-1][2] if ev else None}')
     # per-tile summary for tiles 5..9 of this CTA (steady state)
     tiles = sorted(set(e[1] for e in ev))
-    for tile in tiles[4:9]:
+    for tile in (tiles if len(tiles) <= 10 else tiles[4:9]):
         seq = [(e, c) for e, tl, c in ev if tl == tile]
         print(f'   tile {tile}: ' + ' '.join(f'e{e}@{c}' for e, c in seq))
     if len(tiles) > 6:

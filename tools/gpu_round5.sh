@@ -1,13 +1,18 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu --tb=short -x > gpurun_out/k_all.log 2>&1; echo "rc=$?" >> gpurun_out/k_all.log
-timeout -s KILL 300 python tools/conv_sweep.py > gpurun_out/sweep.log 2>&1
-timeout -s KILL 900 python -m pytest tests/test_gpu_model.py -q -m gpu --tb=short > gpurun_out/model.log 2>&1; echo "rc=$?" >> gpurun_out/model.log
-timeout -s KILL 600 python bench.py --steps 36 --warmup 21 --no-cpu-baseline > gpurun_out/bench_mfid.json 2> gpurun_out/bench_mfid.err; echo "rc=$?" >> gpurun_out/bench_mfid.err
-tail -n 2 gpurun_out/k_all.log gpurun_out/model.log; cat gpurun_out/sweep.log; python - <<'PY'
+timeout -s KILL 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu > gpurun_out/r5_tests.log 2>&1
+tail -3 gpurun_out/r5_tests.log
+timeout -s KILL 100 python tools/conv_trace.py 270 480 > gpurun_out/r5_trace_lr.log 2>&1
+timeout -s KILL 100 python tools/conv_trace.py 540 960 > gpurun_out/r5_trace_2x.log 2>&1
+timeout -s KILL 100 python tools/conv_sweep.py > gpurun_out/r5_sweep.log 2>&1
+timeout -s KILL 300 python tools/profile_kernels.py > gpurun_out/r5_kern.json 2> gpurun_out/r5_kern.err
+timeout -s KILL 200 python bench.py --steps 18 --warmup 3 --no-cpu-baseline > gpurun_out/r5_bench.json 2> gpurun_out/r5_bench.err
+timeout -s KILL 200 python bench.py --steps 18 --warmup 3 --no-cpu-baseline --fuse > gpurun_out/r5_bench_fuse.json 2>> gpurun_out/r5_bench.err
+python - <<'PY'
 import json
-d = json.load(open('gpurun_out/bench_mfid.json'))
-print({k: d[k] for k in ['value','ms_per_step','gpu_launches']}, 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'])
-print('conv', d['roofline']['seconds']*1e6, 'us', d['roofline']['frac'])
-for k,v in d['roofline_other'].items(): print(k, v['seconds']*1e6, 'us', v['achieved'], v['unit'], v['frac'])
+for f in ('r5_bench','r5_bench_fuse'):
+    try:
+        d=json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], d['e2e']['value'], d.get('roofline'))
+    except Exception as e: print(f, 'ERR', e)
 PY
+grep -E '"seconds"|"frac"|name' gpurun_out/r5_kern.json | head -30

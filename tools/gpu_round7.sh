@@ -1,14 +1,19 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 300 python tools/tc_probe.py > gpurun_out/probe.log 2>&1; grep TC_PROBE gpurun_out/probe.log
-timeout -s KILL 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu --tb=short -x > gpurun_out/k_all.log 2>&1; echo "rc=$?" >> gpurun_out/k_all.log
-timeout -s KILL 200 python tools/conv_sweep.py > gpurun_out/sweep1.log 2>&1
-timeout -s KILL 900 python -m pytest tests/test_gpu_model.py -q -m gpu -s --tb=short > gpurun_out/model.log 2>&1; echo "rc=$?" >> gpurun_out/model.log
-timeout -s KILL 600 python bench.py --steps 36 --warmup 21 --no-cpu-baseline > gpurun_out/bench_mfid.json 2> gpurun_out/bench_mfid.err; echo "rc=$?" >> gpurun_out/bench_mfid.err
-tail -n 2 gpurun_out/k_all.log gpurun_out/model.log; cat gpurun_out/sweep1.log; python - <<'PY'
+timeout -s KILL 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "conv" > gpurun_out/r7_tests.log 2>&1
+tail -5 gpurun_out/r7_tests.log
+timeout -s KILL 100 python tools/conv_sweep.py > gpurun_out/r7_sweep.log 2>&1
+REFVSR_NO_KXFOLD=1 timeout -s KILL 100 python tools/conv_sweep.py > gpurun_out/r7_sweep_nofold.log 2>&1
+timeout -s KILL 100 python tools/conv_trace.py 270 480 > gpurun_out/r7_trace_lr.log 2>&1
+
+timeout -s KILL 200 python bench.py --steps 18 --warmup 3 --no-cpu-baseline > gpurun_out/r7_bench.json 2> gpurun_out/r7_bench.err
+REFVSR_NO_KXFOLD=1 timeout -s KILL 200 python bench.py --steps 18 --warmup 3 --no-cpu-baseline > gpurun_out/r7_bench_nofold.json 2>> gpurun_out/r7_bench.err
+python - <<'PY'
 import json
-d = json.load(open('gpurun_out/bench_mfid.json'))
-print({k: d[k] for k in ['value','ms_per_step','gpu_launches']}, 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'])
-print('conv', d['roofline']['seconds']*1e6, 'us', d['roofline']['frac'])
-for k,v in d['roofline_other'].items(): print(k, v['seconds']*1e6, 'us', v['achieved'], v['unit'], v['frac'])
+for f in ('r7_bench','r7_bench_nofold'):
+    try:
+        d=json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], d['e2e']['value'])
+    except Exception as e: print(f, 'ERR', e)
+
 PY
+paste gpurun_out/r7_sweep.log gpurun_out/r7_sweep_nofold.log | awk -F'\t' '{print substr($1,1,75), "| nofold:", substr($2,47,10)}'

@@ -1,6 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 900 python bench.py --steps 36 --warmup 18 > gpurun_out/bench_mfid.json 2> gpurun_out/bench_mfid.err; echo "rc=$?" >> gpurun_out/bench_mfid.err
-timeout -s KILL 600 python bench.py --steps 36 --warmup 18 --workload small_mfid --no-cpu-baseline > gpurun_out/bench_small.json 2> gpurun_out/bench_small.err; echo "rc=$?" >> gpurun_out/bench_small.err
-timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 12 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-tail -n 4 gpurun_out/bench_mfid.err gpurun_out/bench_small.err; cut -c1-1200 gpurun_out/bench_mfid.json; echo; cut -c1-400 gpurun_out/bench_small.json
+timeout -s KILL 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "conv" > gpurun_out/r8_tests.log 2>&1
+tail -3 gpurun_out/r8_tests.log
+timeout -s KILL 300 python bench.py --steps 18 --warmup 3 --no-cpu-baseline > gpurun_out/r8_bench.json 2> gpurun_out/r8_bench.err
+REFVSR_KXFOLD_ALL=1 timeout -s KILL 300 python bench.py --steps 18 --warmup 3 --no-cpu-baseline > gpurun_out/r8_bench_foldall.json 2>> gpurun_out/r8_bench.err
+python - <<'PY'
+import json
+for f in ('r8_bench','r8_bench_foldall'):
+    try:
+        d=json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], d['e2e'], d['clocks'])
+    except Exception as e: print(f, 'ERR', e)
+PY
+tail -5 gpurun_out/r8_bench.err
