@@ -43,7 +43,7 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock / throttle reasons sampled while the timed region runs (NVML every 10 ms, else nvidia-smi every 200 ms)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
@@ -52,7 +52,26 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_ev = index, [], threading.Event()
 
+    def _nvml_loop(self):
+        """NVML directly (nvidia_ml_py): one sample every 10 ms, so even a 0.2 s timed region gets ~20 samples."""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = ((0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'), (0x20, 'sw_thermal_slowdown'), (0x4, 'sw_power_cap'))
+        while not self._stop_ev.is_set():
+            r = int(get_reasons(h))
+            flags = ['Active' if r & bit else 'Not Active' for bit, _ in bits]
+            self.rows.append([str(self.index), str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), '0'] + flags)
+            self._stop_ev.wait(0.01)
+
     def run(self):
+        try:
+            self._nvml_loop()
+            return
+        except Exception:
+            pass                                             # no NVML binding: fall back to the nvidia-smi CLI below
         while not self._stop_ev.is_set():
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
@@ -88,6 +107,16 @@ def make_model(workload, precision, device, graphs=True, fuse=False):
     net = SRNet(cfg).eval()
     seeded_test_weights(net, seed=1234)          # random-init weights of the named architecture (no checkpoints offline)
     return cfg, net.to(device)
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the committed
+    `ncu --set full` capture (profiles/r01_ncu_conv_lr.json); None when the summary is absent."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_ncu_conv_lr.json')) as f:
+            return float(json.load(f)['traffic'])
+    except Exception:
+        return None
 
 
 def host_threads():
@@ -388,7 +417,7 @@ def run_ours(args):
                                  'kernel nodes replayed by the per-window CUDA graphs)',
             'clocks': clocks, 'clocks_e2e': clocks_e2e,
             'roofline': dict(roof['conv3x3_lr'], kernel='conv_tc_kernel 3x3 C->C @270x480 (+ReLU+residual)',
-                             peak_source=peaks['source'], traffic=None),
+                             peak_source=peaks['source'], traffic=ncu_traffic()),
             'roofline_other': {k: v for k, v in roof.items() if k != 'conv3x3_lr'},
         }
         if world == 1 and not args.no_cpu_baseline:
