@@ -169,6 +169,25 @@ __device__ __forceinline__ void issue_taps_box(uint32_t d_tmem, uint64_t ad, uin
   }
 }
 
+// The tiles of one epilogue group, walked without integer divisions: tile index, tile coordinates, and the TMEM
+// accumulator (tile t lives in accumulator t % nacc, phase (t / nacc) & 1; consecutive tiles of a group are NACC apart).
+struct TileIter {
+  int tile, ty, tx, step, dty, dtx;
+  uint32_t acc, accph;
+  __device__ __forceinline__ void init(int first, int step_, int tiles_x, int grp) {
+    tile = first; step = step_;
+    ty = first / tiles_x; tx = first - ty * tiles_x;
+    dty = step_ / tiles_x; dtx = step_ - dty * tiles_x;
+    acc = (uint32_t)grp; accph = 0;
+  }
+  __device__ __forceinline__ void next(int tiles_x, int nacc) {
+    tile += step; tx += dtx; ty += dty;
+    if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+    acc += NACC;
+    if (acc >= (uint32_t)nacc) { acc -= (uint32_t)nacc; accph ^= 1u; }
+  }
+};
+
 // MODE: 0 = 128B-swizzled boxes per (kx, chunk); 1 = single box per (tile, chunk); 2 = 32B-swizzled quads per kx;
 // 3 = "kx-folded" 3x3: tile = 4 rows x 30 columns computed on a 4 x 32 pixel grid (M = 128, one warp per row).  One MMA
 //     per (ky, 16-channel slice) multiplies the grid by the weights of ALL three kx taps at once (N = 3 * NB, the taps
@@ -442,12 +461,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       // is already complete when a group comes back for its next tile, so a prefetch issued just before the tfull wait
       // hides nothing and the L2 / HBM latency of the 96-byte-strided loads lands on the critical path.
       const int nbase = nblk * p.NB;
-      auto tile_pixel = [&](int tile, bool& valid) -> size_t {
-        const int oy = (tile / p.tiles_x) * p.th + q, ox = (tile % p.tiles_x) * p.tw + lane;
-        valid = (tile < ntiles) && (lane < p.tw) && (oy < p.Ho) && (ox < p.Wo);
+      auto tile_pixel = [&](const TileIter& it, bool& valid) -> size_t {
+        const int oy = it.ty * p.th + q, ox = it.tx * p.tw + lane;
+        valid = (it.tile < ntiles) && (lane < p.tw) && (oy < p.Ho) && (ox < p.Wo);
         return valid ? (size_t)oy * p.Wo + ox : 0;
       };
-      uint4 rp[3][2], rn[3][2];
+      uint4 rp[3][2], rn[3][2];                 // residual vectors of the current / next tile
       auto fetch_res = [&](size_t pix, uint4 (&dst)[3][2]) {
         if (res != nullptr) {
 #pragma unroll
@@ -459,26 +478,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
             }
         }
       };
+      TileIter it;
+      it.init(blockIdx.x + grp * gridDim.x, NACC * gridDim.x, p.tiles_x, grp);
       {
         bool v0;
-        const size_t p0 = tile_pixel(blockIdx.x + grp * gridDim.x, v0);
-        fetch_res(p0, rn);
+        fetch_res(tile_pixel(it, v0), rn);
       }
-      for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += NACC * gridDim.x, tl += NACC) {
-        const uint32_t acc = tl % (uint32_t)p.nacc, accph = (tl / (uint32_t)p.nacc) & 1u;
+      for (; it.tile < ntiles; it.next(p.tiles_x, p.nacc)) {
+        const int tile = it.tile; (void)tile;
+        const uint32_t acc = it.acc, accph = it.accph;
         bool valid, valid_next;
-        const size_t pix = tile_pixel(tile, valid);
+        const size_t pix = tile_pixel(it, valid);
 #pragma unroll
         for (int c = 0; c < 3; ++c) { rp[c][0] = rn[c][0]; rp[c][1] = rn[c][1]; }
-        const size_t pix_next = tile_pixel(tile + NACC * gridDim.x, valid_next);
-        fetch_res(pix_next, rn);
+        TileIter nx = it;
+        nx.next(p.tiles_x, p.nacc);
+        fetch_res(tile_pixel(nx, valid_next), rn);
         RV_TRACE(2 + grp, 0, tile);
         tc::mbar_wait(&bar_tfull[acc], accph);
         tc::tc_fence_after();
         RV_TRACE(2 + grp, 1, tile);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {          // 3 * NB <= 256 -> at most 5 chunks; unrolled so rp[] stays in registers
+        for (int c = 0; c < 3; ++c) {          // 9 * NB <= 512 -> at most 3 chunks; unrolled so rp[] stays in registers
           if (c >= nch) break;
           const int n0 = c * 16;
           uint32_t d0[16], d1[16], d2[16];
@@ -567,12 +589,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         const int act_post = (post_slope == 1.f) ? 0 : (post_slope == 0.f ? 1 : 2);
         // residual vectors are fetched one tile ahead (see the MODE 3 branch above)
         const int nbase = nblk * p.NB;
-        auto tile_pixel = [&](int tile, bool& valid) -> size_t {
-          const int oy = (tile / p.tiles_x) * p.th + ty, ox = (tile % p.tiles_x) * p.tw + tx;
-          valid = (tile < ntiles) && (oy < p.Ho) && (ox < p.Wo);
+        auto tile_pixel = [&](const TileIter& it, bool& valid) -> size_t {
+          const int oy = it.ty * p.th + ty, ox = it.tx * p.tw + tx;
+          valid = (it.tile < ntiles) && (oy < p.Ho) && (ox < p.Wo);
           return valid ? (size_t)oy * p.Wo + ox : 0;          // out-of-image lanes read pixel 0, never store
         };
-        uint4 rp[3][2], rn[3][2];
+        uint4 rp[3][2], rn[3][2];               // residual vectors of the current / next tile
         auto fetch_res = [&](size_t pix, uint4 (&dst)[3][2]) {
           if (RV_DBG(p, 128)) {
 #pragma unroll
@@ -587,19 +609,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
               }
           }
         };
+        TileIter it;
+        it.init(blockIdx.x + grp * gridDim.x, NACC * gridDim.x, p.tiles_x, grp);
         {
           bool v0;
-          const size_t p0 = tile_pixel(blockIdx.x + grp * gridDim.x, v0);
-          fetch_res(p0, rn);
+          fetch_res(tile_pixel(it, v0), rn);
         }
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += NACC * gridDim.x, tl += NACC) {
-          const uint32_t acc = tl % (uint32_t)p.nacc, accph = (tl / (uint32_t)p.nacc) & 1u;
+        for (; it.tile < ntiles; it.next(p.tiles_x, p.nacc)) {
+          const int tile = it.tile; (void)tile;
+          const uint32_t acc = it.acc, accph = it.accph;
           bool valid, valid_next;
-          const size_t pix = tile_pixel(tile, valid);
+          const size_t pix = tile_pixel(it, valid);
 #pragma unroll
           for (int c = 0; c < 3; ++c) { rp[c][0] = rn[c][0]; rp[c][1] = rn[c][1]; }
-          const size_t pix_next = tile_pixel(tile + NACC * gridDim.x, valid_next);
-          fetch_res(pix_next, rn);
+          TileIter nx = it;
+          nx.next(p.tiles_x, p.nacc);
+          fetch_res(tile_pixel(nx, valid_next), rn);
           RV_TRACE(2 + grp, 0, tile);
           tc::mbar_wait(&bar_tfull[acc], accph);
           tc::tc_fence_after();
