@@ -221,7 +221,7 @@ struct TileIter {
 #define RV_TRACE(role, ev, tile) do { } while (0)
 #endif
 
-template <typename TI, typename TR, typename TO, int MODE>
+template <typename TI, typename TR, typename TO, int MODE, bool PS = false>   // PS: pixel-shuffle stores on the fast epilogue
 __global__ void __launch_bounds__(32 * (1 + MAX_MMA) + 128 * NACC, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                const TcP p) {
@@ -630,7 +630,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           tc::tc_fence_after();
           RV_TRACE(2 + grp, 1, tile);
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride;
-          for (int c3 = 0; c3 < nch; c3 += 3) {
+          // pixel shuffle: the (a, b) sub-pixel of this thread's pixel receives channels c = n / 4; one 16-n chunk gives it
+          // 4 channels = 8 bytes.  All chunks are packed into ob[] first so each sub-pixel row is written as whole
+          // 16-byte vectors (complete 32-byte sectors) instead of 8-byte pieces.
+          uint32_t ob[PS ? 4 : 1][PS ? 12 : 1];
+          (void)ob;
+#pragma unroll
+          for (int bb = 0; bb < 2; ++bb) {       // NB <= 96: at most two batches of three 16-column chunks
+            const int c3 = bb * 3;
+            if (c3 >= nch) break;
             uint32_t r[3][16];
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -701,12 +709,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                 for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], -3.f), 3.f);
               }
               if (valid && !RV_DBG(p, 64)) {
-                uint4 o0, o1;
-                o0.x = pack2(v[0], v[1], TO()); o0.y = pack2(v[2], v[3], TO()); o0.z = pack2(v[4], v[5], TO()); o0.w = pack2(v[6], v[7], TO());
-                o1.x = pack2(v[8], v[9], TO()); o1.y = pack2(v[10], v[11], TO()); o1.z = pack2(v[12], v[13], TO()); o1.w = pack2(v[14], v[15], TO());
-                uint4* o = reinterpret_cast<uint4*>(out + pix * p.out_cs + nbase + n0);
-                o[0] = o0;
-                o[1] = o1;
+                if constexpr (PS) {
+                  // n = 4c + 2a + b: value v[4 * cc + ab] is channel (n0 / 4 + cc) of sub-pixel ab
+#pragma unroll
+                  for (int ab = 0; ab < 4; ++ab) {
+                    ob[ab][2 * (bb * 3 + c)] = pack2(v[ab], v[4 + ab], TO());
+                    ob[ab][2 * (bb * 3 + c) + 1] = pack2(v[8 + ab], v[12 + ab], TO());
+                  }
+                } else {
+                  uint4 o0, o1;
+                  o0.x = pack2(v[0], v[1], TO()); o0.y = pack2(v[2], v[3], TO()); o0.z = pack2(v[4], v[5], TO()); o0.w = pack2(v[6], v[7], TO());
+                  o1.x = pack2(v[8], v[9], TO()); o1.y = pack2(v[10], v[11], TO()); o1.z = pack2(v[12], v[13], TO()); o1.w = pack2(v[14], v[15], TO());
+                  uint4* o = reinterpret_cast<uint4*>(out + pix * p.out_cs + nbase + n0);
+                  o[0] = o0;
+                  o[1] = o1;
+                }
+              }
+            }
+          }
+          if constexpr (PS) {
+            if (valid && !RV_DBG(p, 64)) {
+              const int oy = it.ty * p.th + ty, ox = it.tx * p.tw + tx;
+#pragma unroll
+              for (int ab = 0; ab < 4; ++ab) {
+                TO* o = out + ((size_t)(2 * oy + (ab >> 1)) * (2 * p.Wo) + (2 * ox + (ab & 1))) * p.out_cs + (nbase >> 2);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)          // 2 chunks = 8 channels = 16 bytes per vector
+                  if (2 * k + 1 < nch) reinterpret_cast<uint4*>(o)[k] = make_uint4(ob[ab][4 * k], ob[ab][4 * k + 1], ob[ab][4 * k + 2], ob[ab][4 * k + 3]);
               }
             }
           }
@@ -869,10 +898,10 @@ static int make_act_tmap(CUtensorMap* m, const void* ptr, int C, int W, int H, i
 static int g_num_sms = 0;
 static int g_max_smem = 0;
 
-template <typename TI, typename TR, typename TO, int MODE>
+template <typename TI, typename TR, typename TO, int MODE, bool PS = false>
 static int launch_tc_mode(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& p, dim3 grid, size_t smem,
                      cudaStream_t st) {
-  auto kern = conv_tc_kernel<TI, TR, TO, MODE>;
+  auto kern = conv_tc_kernel<TI, TR, TO, MODE, PS>;
   static size_t configured = 0;   // per template instantiation
   if (smem > configured) {
     RV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -898,6 +927,9 @@ template <typename TI, typename TR, typename TO>
 static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& p, dim3 grid, size_t smem, cudaStream_t st) {
   if (p.sw32) return launch_tc_mode<TI, TR, TO, 2>(tm0, tm1, p, grid, smem, st);
   if (p.fold) return launch_tc_mode<TI, TR, TO, 3>(tm0, tm1, p, grid, smem, st);
+  if constexpr (sizeof(TO) == 2) {
+    if (p.fast && p.pixel_shuffle && p.single_box) return launch_tc_mode<TI, TR, TO, 1, true>(tm0, tm1, p, grid, smem, st);
+  }
   if (p.single_box) return launch_tc_mode<TI, TR, TO, 1>(tm0, tm1, p, grid, smem, st);
   return launch_tc_mode<TI, TR, TO, 0>(tm0, tm1, p, grid, smem, st);
 }
@@ -934,7 +966,9 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   auto al16 = [](const void* q, int cs, int dt) { return q == nullptr || (((uintptr_t)q % 16 == 0) && ((cs * dtype_size(dt)) % 16 == 0)); };
   p.vec_ok = al16(d->out, d->out_cs, d->out_dtype) && al16(d->gate, d->gate_cs, d->in_dtype) && al16(d->res, d->res_cs, rdt);
   static const bool fast_ok = getenv("REFVSR_NO_FAST_EPILOGUE") == nullptr;
-  p.fast = fast_ok && p.vec_ok && !d->pixel_shuffle && (d->cout % p.NB == 0) && d->out_dtype != RV_F32 && rdt != RV_F32 &&
+  // (pixel-shuffle outputs: 8-byte stores of 4 channels, so (cout / 4) channels per pixel must keep them 8-byte aligned)
+  const bool ps_ok = !d->pixel_shuffle || ((d->layout == 1 || d->layout == 3) && p.NB % 32 == 0 && p.NB <= 96 && (d->out_cs * 2) % 16 == 0 && d->res == nullptr && d->gate == nullptr && (d->out_cs * 2) % 8 == 0 && ((uintptr_t)d->out % 8) == 0);
+  p.fast = fast_ok && p.vec_ok && ps_ok && (d->cout % p.NB == 0) && d->out_dtype != RV_F32 && rdt != RV_F32 &&
            d->out_dtype == d->in_dtype && rdt == d->in_dtype && (p.dbg & 31) == 0;   // knock-out bits 32/64/128 are fast-path experiments
   // mode 1 (single box per tile and chunk) when the whole weight set stays resident next to >= 2 boxes
   p.single_box = 0; p.sw32 = 0; p.nq0 = p.nq1 = 0; p.q_bytes = 0; p.fold = 0;
@@ -949,7 +983,7 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
     // 48 -> 48 convs, whose epilogue (heavier when folded: 3x TMEM reads + shuffles) already paces the kernel
     static const bool fold_all = getenv("REFVSR_KXFOLD_ALL") != nullptr;
     const bool fold_pays = fold_all || (p.nch0 + p.nch1) >= 2 || p.NB <= 32;
-    p.fold = fold_ok && fold_pays && d->layout == 1 && d->kh == 3 && p.fast && p.dbg == 0 && 9 * p.NB <= 512 /* three N = 3 * NB accumulators in TMEM */ && w_fold + 3 * (size_t)(6 * 32 * 128) <= budget;
+    p.fold = fold_ok && fold_pays && !d->pixel_shuffle && d->layout == 1 && d->kh == 3 && p.fast && p.dbg == 0 && 9 * p.NB <= 512 /* three N = 3 * NB accumulators in TMEM */ && w_fold + 3 * (size_t)(6 * 32 * 128) <= budget;
   }
   if (p.fold) {
     p.th = 4; p.tw = 30; p.tw_shift = 0;
