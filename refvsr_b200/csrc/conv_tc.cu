@@ -1,24 +1,23 @@
 // tcgen05 / TMEM implicit-GEMM convolution for NHWC f16/bf16 activations (stride 1, "same"-style
 // zero padding), the tensor-core implementation of rv_conv2d.
 //
-// GEMM view per CTA tile: M = 128 output pixels (an 8 x 16 patch), N = NB output channels,
-// K = kw * (64-channel chunks of src0|src1) stages, each stage contributing kh taps x (<=4) UMMA_K=16
-// steps.  There is no im2col buffer:
-//   * A operand: for every (kx, channel-chunk) ONE TMA box load of (8+kh-1) x 16 pixels x 64
-//     channels at x-offset (x0 + kx - pad), y-offset (y0 - pad).  TMA's out-of-bounds zero fill
-//     implements the convolution's zero padding and the channel padding to 64.  The box lands in
-//     shared memory as 128-byte pixel rows with the 128B swizzle, i.e. directly in the canonical
-//     K-major UMMA layout; the kh vertical taps are row-shifted views of the same box
-//     (+ky*16 rows = +ky*2048 bytes, which preserves the swizzle phase).
-//   * B operand: weights pre-packed on the host in exactly the swizzled shared-memory image
-//     ([stage][ky][NB][64]), fetched with plain bulk copies; resident for the whole CTA lifetime when
-//     they fit, otherwise streamed through the same ring as A.
-//   * D: fp32 accumulators in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of
-//     tile i+1.  Persistent CTAs walk the tile list round-robin.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2-9 = two epilogue groups of
-// four warps; group g drains accumulator buffer g (tiles of parity g), so two tiles are in their epilogue
-// at any time while the MMA warp fills the next one (tcgen05.ld -> bias/act/gate/residual -> NHWC or
-// pixel-shuffled store).  The epilogue math is branch-free and fully unrolled (registers only).
+// GEMM view per CTA tile: M = 128 output pixels, N = NB output channels (3 * NB in the kx-folded mode), K = taps x
+// 64-channel chunks of src0|src1 in UMMA_K = 16 steps.  There is no im2col buffer:
+//   * A operand: TMA box loads of the tile + halo, 64 channels wide.  TMA's out-of-bounds zero fill implements the
+//     convolution's zero padding and the channel padding to 64.  The box lands in shared memory as 128-byte pixel rows
+//     with the 128B swizzle, i.e. directly in the canonical K-major UMMA layout, and the taps are row-shifted
+//     descriptor views of it (the swizzle is a pure function of the shared-memory address, so any view that starts
+//     on a 128-byte row is valid with base_offset 0 - measured, profiles/r01_umma_base_offset_experiment.log).
+//     Layout 0: one box per (kx, chunk), tile 8 x 16; layout 1 (default): ONE box per (tile, chunk), tile 16 x 8,
+//     all kh x kw taps are views; MODE 3: tile 4 x 30 on a 4 x 32 grid, kx folded into N (see the kernel comment).
+//   * B operand: weights pre-packed on the host in exactly the swizzled shared-memory image, fetched with plain bulk
+//     copies; resident for the whole CTA lifetime when they fit, otherwise streamed through the same ring as A.
+//   * D: fp32 accumulators in TMEM (3 or 6 buffers).  Persistent CTAs walk the tile list round-robin.
+// Warp roles (512 threads): warp 0 = TMA producer, warps 1-3 = MMA issuers (alternate tiles; warp-uniform control flow,
+// an elected lane issues - see tc::elect_one), warps 4-15 = three epilogue groups of four warps; group g drains the
+// tiles t = g, g + 3, ... (tcgen05.ld -> bias/act/gate/residual -> NHWC or pixel-shuffled store).  setmaxnreg moves
+// registers from the four role warps (40) to the epilogue warps (152).  How this shape was arrived at, with device
+// timelines and knock-outs: profiles/r01_conv_timeline.md.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -51,11 +50,10 @@ struct TcP {
   uint32_t tmem_cols, acc_stride;
   // tile geometry: mode 0 = 8 rows x 16 cols, one box per (kx, chunk) stage (y-halo only);
   //                mode 1 = 16 rows x 8 cols, ONE box per (chunk) stage with x- and y-halo, taps = shifted views
-  int single_box, th, tw, tw_shift, bw;   // bw = box width in pixels (mode 1: 8 or 16)
+  int single_box, th, tw, tw_shift, bw;   // bw = box width in pixels (mode 1: tile + halo, mode 3: 32)
   int bo_force;                           // experiment hook: constant base_offset for kx != 0 taps (-1 = kx)
   // layout 2: operands staged with SWIZZLE_32B in 16-channel quads (32-byte rows): one UMMA_K = 16 slice is a
-  // whole row, so each tcgen05.mma fetches exactly its operand bytes (with 128-byte rows every K-slice pulls the
-  // full row: ~110 cycles per MMA at N = 48, measured - profiles/r01_conv_knockout.md)
+  // whole row (built to test an operand over-fetch hypothesis; measured no faster, kept as a validated variant)
   int nacc;                               // accumulator buffers in TMEM (3 or 6)
   int fold;                               // mode 3: the 3 kx taps folded into N = 3 * NB (see conv_tc_kernel MODE 3)
   int fast;                               // streamlined epilogue (all-16-bit, vector stores, full 16-channel chunks)
