@@ -87,3 +87,33 @@ def test_space_to_depth_reindexing_equals_stride2_conv(k, srcs, oracle_ops):
     out = torch.zeros(6, 9, 7)
     oracle_ops.conv2d(layer, zs[0], zs[1] if len(zs) > 1 else None, out)
     assert (out - exp).abs().max() < 1e-4
+
+
+def test_layout1_image_is_tap_major_and_layout3_is_the_same_image():
+    """layout 1 = [nblk][chunk][ky][kx][NB][64]: the three kx taps of one ky are ADJACENT row blocks, which is what the
+    kx-folded conv mode multiplies as one N = 3 * NB operand (conv_tc.cu MODE 3); layout 3 is the same image with the
+    folding disabled."""
+    cout, cin, k, nb = 48, 48, 3, 48
+    w = torch.randn(cout, cin, k, k).half().float()
+    p1 = packing.pack_tc(w, [(cin, cin)], torch.float16, nb, layout=1)
+    p3 = packing.pack_tc(w, [(cin, cin)], torch.float16, nb, layout=3)
+    assert torch.equal(p1, p3)
+    assert tuple(p1.shape) == (1, 1, k * k, nb, 64)
+    t = p1.float().view(k * k, nb, 8, 8)
+    for ky in range(k):
+        for kx in range(k):
+            for n in (0, 7, 13, 47):
+                row = torch.stack([t[ky * k + kx, n, j ^ (n % 8)] for j in range(8)]).reshape(64)
+                assert torch.equal(row[:cin], w[n, :, ky, kx]), (ky, kx, n)
+
+
+def test_choose_layout_defaults_and_env(monkeypatch):
+    monkeypatch.delenv('REFVSR_TC_LAYOUT', raising=False)
+    assert packing.choose_layout(3, 3, [(48, 48)], 48) == 1                      # taps resident -> one box per tile
+    assert packing.choose_layout(7, 7, [(64, 64)], 64) == 0                      # 49 taps x 64 x 128 B do not fit
+    assert packing.choose_layout(3, 5, [(48, 48)], 48) == 0                      # non-square kernels: layout 0
+    monkeypatch.setenv('REFVSR_TC_LAYOUT', '3')
+    assert packing.choose_layout(3, 3, [(48, 48)], 48) == 3
+    assert packing.choose_layout(7, 7, [(64, 64)], 64) == 0
+    monkeypatch.setenv('REFVSR_TC_LAYOUT', '0')
+    assert packing.choose_layout(3, 3, [(48, 48)], 48) == 0
