@@ -141,6 +141,16 @@ int rv_spynet_resize_norm(const float* src_nchw, int H, int W, float* out, int H
                           void* stream);
 /* 2x2 mean pool, HWC fp32 with C channels (SPyNet.py:66-78) */
 int rv_avgpool2(const float* src, int H, int W, int C, float* out, void* stream);
+/* 2x2 / stride 2 max pool of an NHWC map (torchvision vgg19.features[4] inside FeatureMatching with vgg_range = 7,
+ * i.e. the flag_HD_in "8K" configs, attention.py:31-40).  src (H,W,C) -> out (H/2,W/2,C), same dtype. */
+int rv_maxpool2(const void* src, int H, int W, int C, int dtype, void* out, void* stream);
+/* Resize of `n` planar fp32 maps (n,H,W) -> (n,Ho,Wo) with the source coordinate scale `inv_scale` = 1 / scale_factor:
+ *   mode 0: bicubic, A = -0.75, align_corners=False, clamped taps (F.interpolate(mode='bicubic')): the x4 upsample
+ *           of the relevance map (attention.py:96-98) and lr_down = bicubic x0.5 of the LR frame (RefVSR.py:125);
+ *   mode 1: nearest, src = floor(dst * inv_scale) (F.interpolate(scale_factor=0.5, mode='nearest'), attention.py:65-67).
+ * clamp01: clamp the result to [0,1] (both bicubic call sites do). */
+int rv_resize_planes(const float* src, int n, int H, int W, float inv_scale, int Ho, int Wo, int mode, int clamp01,
+                     float* out, void* stream);
 /* One pyramid level's network input (SPyNet.py:84-102):
  *   flow_up = level0 ? 0 : 2 * bilinear_x2_align_corners(flow_prev)      -> flow_up (H,W,2) fp32
  *   out8    = [ref(3), flow_warp(supp, flow_up, border, align_corners=True)(3), flow_up(2)]

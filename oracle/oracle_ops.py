@@ -103,6 +103,21 @@ class OracleOps:
     def avgpool2(self, src, out):
         out.copy_(_nhwc(O.avgpool2(_nchw(src))))
 
+    def maxpool2(self, src, out):
+        out.copy_(_nhwc(O.maxpool2(_nchw(src).float())).to(out.dtype))
+
+    def resize_planes(self, src, out, inv_scale, mode='bicubic', clamp01=False):
+        x = src.float().unsqueeze(0)
+        if mode == 'bicubic':
+            y = O.bicubic(x, 1.0 / inv_scale)
+        else:
+            assert inv_scale == 2.0
+            y = O.nearest_down2(x)
+        if clamp01:
+            y = y.clamp(0, 1)
+        assert tuple(y.shape[1:]) == tuple(out.shape), (y.shape, out.shape)
+        out.copy_(y[0])
+
     def spynet_level_input(self, ref, supp, flow_prev, out8, flow_up):
         H, W = ref.shape[:2]
         fu = torch.zeros(1, 2, H, W) if flow_prev is None else O.bilinear_up2_align_corners(_nchw(flow_prev)) * 2.0

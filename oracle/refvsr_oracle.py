@@ -96,6 +96,20 @@ def bicubic(x, scale):
     return (cols * wy.view(Ho, 4, 1)).sum(-2)
 
 
+def nearest_down2(x):
+    """F.interpolate(x, scale_factor=0.5, mode='nearest') (attention.py:65-67, flag_HD_in): src = floor(dst * 2)"""
+    H, W = x.shape[-2:]
+    return x[..., 0:2 * (H // 2):2, 0:2 * (W // 2):2]
+
+
+def maxpool2(x):
+    """nn.MaxPool2d(2, 2), torchvision vgg19.features[4] (attention.py:31-40 with vgg_range = 7)"""
+    H, W = x.shape[-2:]
+    x = x[..., :2 * (H // 2), :2 * (W // 2)]
+    return torch.maximum(torch.maximum(x[..., 0::2, 0::2], x[..., 0::2, 1::2]),
+                         torch.maximum(x[..., 1::2, 0::2], x[..., 1::2, 1::2]))
+
+
 def avgpool2(x):
     """F.avg_pool2d(x, 2, 2) (SPyNet.py:66-78; attention.py:51)"""
     H, W = x.shape[-2:]
@@ -241,13 +255,16 @@ def lrelu(x, s):
 # the model
 # --------------------------------------------------------------------------------------------------
 class OracleRefVSR:
-    """Functional restatement of models/archs/RefVSR.py::Network for scale 4, flag_HD_in False.
+    """Functional restatement of models/archs/RefVSR.py::Network for scale 4, flag_HD_in False or True (the "8K"
+    configs: matching on 1/4-resolution VGG[0:7] features, matching_ksize 8, both alignment levels with AlignedConv2d).
     `sd` is a state_dict with the reference's keys ('Network.' prefix optional)."""
 
     def __init__(self, config, sd):
         self.cfg = config
         self.C = config.mid_channels
         self.nb = config.num_blocks
+        self.hd = bool(getattr(config, 'flag_HD_in', False))
+        self.mk = int(getattr(config, 'matching_ksize', 2))       # config_RefVSR_*.py:31-39: 2, or 2 * scale with flag_HD_in
         self.sd = {(k[len('Network.'):] if k.startswith('Network.') else k): v.detach().float().cpu()
                    for k, v in sd.items()}
         self.frame_itr_num = 0
@@ -310,37 +327,57 @@ class OracleRefVSR:
     # ---- FeatureMatching (attention.py:58-100) ----
     def match_features(self, x, pool):
         x = F.conv2d(x, self.sd['feature_match.sub_mean.weight'], self.sd['feature_match.sub_mean.bias'])
+        if self.hd:
+            x = nearest_down2(x)                                           # attention.py:65-67
         if pool:
             x = avgpool2(x)
         x = torch.relu(self.conv('feature_match.feature_extract.0', x))
         x = torch.relu(self.conv('feature_match.feature_extract.2', x))
+        if self.hd:                                                        # vgg_range = 7: maxpool, conv 64->128, relu
+            x = torch.relu(self.conv('feature_match.feature_extract.5', maxpool2(x)))
+            return lrelu(self.conv('feature_match.feature_extract.map128.0', x), 0.2)
         return lrelu(self.conv('feature_match.feature_extract.map64.0', x), 0.2)
 
     def feature_match(self, lr, ref):
-        return match_argmax(self.match_features(lr, False), self.match_features(ref, True))
+        conf, idx = match_argmax(self.match_features(lr, False), self.match_features(ref, True))
+        h, hc = lr.shape[-2], conf.shape[-2]
+        if h != hc:                                                        # attention.py:96-98
+            conf = bicubic(conf, h / hc).clamp(0, 1)
+        return conf, idx
 
     # ---- AlignedAttention / AlignedConv2d ----
-    def align_conv1(self, x):                      # alignment.py:19,42-43
-        a = lrelu(self.conv('aa2.align.conv1.0', x, pad=2), 0.2)
-        return lrelu(self.resblock('aa2.align.conv1.2', a), 0.2)
+    def align_conv1(self, x, aa='aa2'):            # alignment.py:19,42-43
+        a = lrelu(self.conv(aa + '.align.conv1.0', x, pad=2), 0.2)
+        return lrelu(self.resblock(aa + '.align.conv1.2', a), 0.2)
 
-    def aa2(self, lr, ref, idx, value):            # attention.py:131-159 with scale=2, align=True
+    def aligned_attention(self, aa, scale, align, lr, ref, idx, value):
+        """attention.py:131-159: the output has twice the size of `lr`; blocks of scale x scale pixels of `value` (and,
+        with align, of `ref` - indexed on ITS OWN block grid, as the reference does) are gathered by `idx`, then
+        resampled by the per-block affine map of AlignedConv2d (kernel = stride = scale)."""
         n, _, h, w = lr.shape
-        warped = gather_blocks(value, idx, h, w, 2)
-        warped_ref = gather_blocks(ref, idx, h, w, 2)
-        query = self.align_conv1(bicubic(lr, 2))
-        rf = self.align_conv1(warped_ref)
-        p = lrelu(self.conv('aa2.align.p_conv.0', torch.cat([rf, query], 1), stride=2, pad=2), 0.2)
-        p = lrelu(self.resblock('aa2.align.p_conv.2', p), 0.2)
-        affine = (self.conv('aa2.align.p_conv.4', p, pad=0) + 1.0).clamp(-3, 3)
+        hq, wq = 2 * h // scale, 2 * w // scale
+        warped = gather_blocks(value, idx, hq, wq, scale)
+        if not align:
+            return warped
+        warped_ref = gather_blocks(ref, idx, hq, wq, scale)
+        query = self.align_conv1(bicubic(lr, 2), aa)
+        rf = self.align_conv1(warped_ref, aa)
+        p = lrelu(self.conv(aa + '.align.p_conv.0', torch.cat([rf, query], 1), stride=scale, pad=2), 0.2)
+        p = lrelu(self.resblock(aa + '.align.p_conv.2', p), 0.2)
+        affine = (self.conv(aa + '.align.p_conv.4', p, pad=0) + 1.0).clamp(-3, 3)
         if self.trace is not None:
             self.trace.setdefault('affine', []).append(affine)
-        return aligned_sample(warped, affine, 2)
+        return aligned_sample(warped, affine, scale)
+
+    def aa2(self, lr, ref, idx, value):            # RefVSR.py:38: AlignedAttention(scale=matching_ksize, align=True)
+        return self.aligned_attention('aa2', self.mk, True, lr, ref, idx, value)
 
     # ---- RAP (RefVSR.py:123-149) ----
     def rap(self, lr, ref, conf, conf_prop, idx, feat_prop, feat_prop_UP, ref_feat_down, ref_feat):
         n, _, h, w = lr.shape
-        aligned = gather_blocks(ref_feat_down, idx, h, w, 1)              # aa1: scale 1, align False
+        s1 = self.mk // 2                                                 # RefVSR.py:37: aa1 scale, align iff > 1
+        lr_down = bicubic(lr, 0.5).clamp(0, 1)                            # RefVSR.py:125
+        aligned = self.aligned_attention('aa1', s1, s1 > 1, lr_down, ref, idx, ref_feat_down)
         alpha = self.basic2('conf_fusion', torch.cat([conf_prop, conf], 1))
         feat_prop = feat_prop + alpha * self.basic2('feat_fusion', torch.cat([feat_prop, aligned], 1))
         feat_prop = self.reslist('feat_decoder', 8, feat_prop)

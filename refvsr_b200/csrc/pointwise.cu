@@ -522,6 +522,38 @@ __device__ __forceinline__ float bicubic_planar(const float* __restrict__ s, int
   return acc;
 }
 
+__global__ void resize_planes_kernel(const float* __restrict__ src, int n, int H, int W, float inv_scale, int Ho,
+                                     int Wo, int mode, int clamp01, float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * Ho * Wo) return;
+  int c = (int)(i / ((long long)Ho * Wo));
+  int p = (int)(i - (long long)c * Ho * Wo);
+  int Y = p / Wo, X = p - Y * Wo;
+  const float* s = src + (size_t)c * H * W;
+  float v;
+  if (mode == 0) {
+    v = bicubic_planar(s, H, W, Y, X, inv_scale);
+  } else {
+    int sy = min((int)floorf((float)Y * inv_scale), H - 1), sx = min((int)floorf((float)X * inv_scale), W - 1);
+    v = s[(size_t)sy * W + sx];
+  }
+  if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+  out[i] = v;
+}
+
+template <typename T>
+__global__ void maxpool2_kernel(const T* __restrict__ src, int H, int W, int C, T* __restrict__ out) {
+  int Ho = H / 2, Wo = W / 2;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Ho * Wo * C) return;
+  int c = (int)(i % C);
+  int p = (int)(i / C);
+  int y = p / Wo, x = p - y * Wo;
+  const T* s = src + ((size_t)(2 * y) * W + 2 * x) * C + c;
+  float v = fmaxf(fmaxf(to_f(s[0]), to_f(s[C])), fmaxf(to_f(s[(size_t)W * C]), to_f(s[(size_t)W * C + C])));
+  out[i] = from_f<T>(v);
+}
+
 template <typename T>
 __global__ void bicubic_up2_image_kernel(const float* __restrict__ src, int H, int W,
                                          T* __restrict__ out, int out_c) {
@@ -738,6 +770,24 @@ extern "C" int rv_bicubic_up2_image(const float* src, int H, int W, void* out, i
   RV_DISPATCH_DTYPE(out_dtype, T, (bicubic_up2_image_kernel<T><<<cdiv(4LL * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
                                       src, H, W, (T*)out, out_c)));
   RV_LAUNCH_CHECK("bicubic_up2_image");
+  return RV_OK;
+}
+
+extern "C" int rv_maxpool2(const void* src, int H, int W, int C, int dtype, void* out, void* stream) {
+  RV_REQUIRE(src && out && H >= 2 && W >= 2 && C > 0, "rv_maxpool2: bad arguments");
+  long long n = (long long)(H / 2) * (W / 2) * C;
+  RV_DISPATCH_DTYPE(dtype, T, (maxpool2_kernel<T><<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)src, H, W, C, (T*)out)));
+  RV_LAUNCH_CHECK("maxpool2");
+  return RV_OK;
+}
+
+extern "C" int rv_resize_planes(const float* src, int n, int H, int W, float inv_scale, int Ho, int Wo, int mode,
+                                int clamp01, float* out, void* stream) {
+  RV_REQUIRE(src && out && n > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && inv_scale > 0.f && (mode == 0 || mode == 1),
+             "rv_resize_planes: bad arguments");
+  long long tot = (long long)n * Ho * Wo;
+  resize_planes_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(src, n, H, W, inv_scale, Ho, Wo, mode, clamp01, out);
+  RV_LAUNCH_CHECK("resize_planes");
   return RV_OK;
 }
 

@@ -56,6 +56,8 @@ SIGNATURES = {
     'rv_prep_image': (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _P]),
     'rv_spynet_resize_norm': (_I, [_P, _I, _I, _P, _I, _I, _P]),
     'rv_avgpool2': (_I, [_P, _I, _I, _I, _P, _P]),
+    'rv_maxpool2': (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    'rv_resize_planes': (_I, [_P, _I, _I, _I, _F, _I, _I, _I, _I, _P, _P]),
     'rv_spynet_level_input': (_I, [_P, _P, _P, _I, _I, _P, _I, _P, _P]),
     'rv_flow_resize': (_I, [_P, _I, _I, _P, _I, _I, _P]),
     'rv_warp': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
@@ -199,6 +201,21 @@ class CudaOps:
         _chk_dev(src, out)
         _check(self.lib, self.lib.rv_avgpool2(_ptr(src), src.shape[0], src.shape[1], src.shape[2], _ptr(out),
                                               self._stream()), 'rv_avgpool2')
+
+    def maxpool2(self, src, out):
+        """NHWC (H,W,C) -> (H/2,W/2,C) 2x2 max (vgg19.features[4], flag_HD_in matching)"""
+        _chk_dev(src, out)
+        assert src.dtype == out.dtype and tuple(out.shape) == (src.shape[0] // 2, src.shape[1] // 2, src.shape[2])
+        _check(self.lib, self.lib.rv_maxpool2(_ptr(src), src.shape[0], src.shape[1], src.shape[2], DTYPE_CODE[src.dtype],
+                                              _ptr(out), self._stream()), 'rv_maxpool2')
+
+    def resize_planes(self, src, out, inv_scale, mode='bicubic', clamp01=False):
+        """planar fp32 (n,H,W) -> (n,Ho,Wo): F.interpolate(scale_factor=1/inv_scale, mode=bicubic|nearest) [+ clamp(0,1)]"""
+        _chk_dev(src, out)
+        assert src.dtype == out.dtype == torch.float32 and src.dim() == 3 and out.dim() == 3 and src.shape[0] == out.shape[0]
+        _check(self.lib, self.lib.rv_resize_planes(_ptr(src), src.shape[0], src.shape[1], src.shape[2], float(inv_scale),
+                                                   out.shape[1], out.shape[2], 0 if mode == 'bicubic' else 1,
+                                                   int(clamp01), _ptr(out), self._stream()), 'rv_resize_planes')
 
     def spynet_level_input(self, ref, supp, flow_prev, out8, flow_up):
         _chk_dev(ref, supp, flow_prev, out8, flow_up)

@@ -45,12 +45,12 @@ class Network(nn.Module):
         self.scale = config.scale
         self.flag_HD_in = config.flag_HD_in
         self.mid_channels = config.mid_channels
-        if self.scale != 4 or self.flag_HD_in:
-            # RefVSR_*_8K (flag_HD_in, aa1 scale 4 / aa2 scale 8, VGG[0:7]) and the x2 models are the
-            # next rows of the scope table; fail loudly instead of silently computing something else.
-            raise NotImplementedError('refvsr_b200 round 1 implements the x4, flag_HD_in=False models '
-                                      '(config_RefVSR_{small_,}{L1,MFID}); got scale=%s flag_HD_in=%s'
-                                      % (self.scale, self.flag_HD_in))
+        if self.scale != 4:
+            # the x2 models are a further row of the scope table; fail loudly instead of silently computing
+            # something else.  flag_HD_in (the "8K" configs: VGG[0:7] matching at 1/4 resolution, matching_ksize 8,
+            # AlignedConv2d on both alignment levels) is handled by the same schedule.
+            raise NotImplementedError('refvsr_b200 implements the x4 models (config_RefVSR_{small_,}{L1,MFID}{,_8K}); '
+                                      'got scale=%s' % (self.scale,))
         build_parameter_tree(self, config)
 
         # cross-call recurrent state (RefVSR.py:96-101), one entry per batch element
@@ -256,31 +256,51 @@ class Network(nn.Module):
         return self._mat12
 
     def _match_features(self, img, pool2, tag):
-        H, W = (img.shape[1] // 2, img.shape[2] // 2) if pool2 else (img.shape[1], img.shape[2])
         dt = self.act_dtype
+        if self.flag_HD_in:                                   # attention.py:65-67: nearest x0.5 before anything else
+            small = self._buf(tag + '.nn', (3, img.shape[1] // 2, img.shape[2] // 2), torch.float32)
+            self.ops.resize_planes(img, small, 2.0, mode='nearest')
+            img = small
+        H, W = (img.shape[1] // 2, img.shape[2] // 2) if pool2 else (img.shape[1], img.shape[2])
         x8 = self._buf(tag + '.x8', (H, W, 8), dt)
         self.ops.prep_image(img, x8, mat12=self._sub_mean_mat(), pool2=pool2)
         f1 = self._conv('feature_match.feature_extract.0', x8, None, self._buf(tag + '.f1', (H, W, 64), dt),
                         [(3, 8)], act_pre=ACT_RELU)
         f2 = self._conv('feature_match.feature_extract.2', f1, None, self._buf(tag + '.f2', (H, W, 64), dt),
                         [(64, 64)], act_pre=ACT_RELU)
+        if self.flag_HD_in:                                   # vgg_range = 7 (attention.py:31-40): maxpool, conv 64->128, ReLU
+            Hm, Wm = H // 2, W // 2
+            mp = self._buf(tag + '.mp', (Hm, Wm, 64), dt)
+            self.ops.maxpool2(f2, mp)
+            f5 = self._conv('feature_match.feature_extract.5', mp, None, self._buf(tag + '.f5', (Hm, Wm, 128), dt),
+                            [(64, 64)], act_pre=ACT_RELU)
+            return self._conv('feature_match.feature_extract.map128.0', f5, None, self._buf(tag + '.f3', (Hm, Wm, 16), dt),
+                              [(128, 128)], act_pre=ACT_LRELU02)
         f3 = self._conv('feature_match.feature_extract.map64.0', f2, None, self._buf(tag + '.f3', (H, W, 16), dt),
                         [(64, 64)], act_pre=ACT_LRELU02)
         return f3
 
     def _feature_match(self, lr, ref, conf, idx):
-        """conf (h,w) fp32, idx (h*w,) int32 indexing the (hr/2 x wr/2) reference feature grid."""
+        """conf (h,w) fp32, idx (hm*wm,) int32 indexing the reference feature grid; (hm, wm) = (h, w), or
+        (h/4, w/4) with flag_HD_in, where the relevance map is then bicubic-upsampled x4 (attention.py:93-98)."""
         h, w = lr.shape[1], lr.shape[2]
         split = self.match_mode == 'split'
         kpad = 448 if split else 192
         lr_f = self._match_features(lr, False, 'fm.lr')
-        A = self._buf('fm.A', (h * w, kpad), torch.float16)
+        hm, wm = lr_f.shape[0], lr_f.shape[1]
+        conf_out = conf
+        if (hm, wm) != (h, w):
+            conf = self._buf('fm.conf_small', (hm, wm), torch.float32)
+        A = self._buf('fm.A', (hm * wm, kpad), torch.float16)
         self.ops.patch_pack(lr_f, A, 1 if split else 0)
         ref_f = self._match_features(ref, True, 'fm.ref')
         R = ref_f.shape[0] * ref_f.shape[1]
         B = self._buf('fm.B', (R, kpad), torch.float16)
         self.ops.patch_pack(ref_f, B, 2 if split else 0)
         self.ops.match_argmax(A, B, conf, idx, impl=1 if self.prefer_tc else 0)
+        if conf is not conf_out:
+            self.ops.resize_planes(conf.view(1, hm, wm), conf_out.view(1, h, w), float(hm) / float(h), mode='bicubic',
+                                   clamp01=True)
 
     # ---- reference encoders (RefVSR.py:233-234,274-275) ----------------------------------------------
     def _ref_features(self, ref):
@@ -301,35 +321,39 @@ class Network(nn.Module):
         return ref8, ref_feat, ref_feat_down
 
     # ---- AlignedConv2d (alignment.py:39-100) --------------------------------------------------------
-    def _align_conv1(self, x8, out, tag):
+    def _align_conv1(self, aa, x8, out, tag):
         H, W = x8.shape[0], x8.shape[1]
         dt = self.act_dtype
-        a = self._conv('aa2.align.conv1.0', x8, None, self._buf(tag + '.a', (H, W, 32), dt), [(3, 8)],
+        a = self._conv(aa + '.align.conv1.0', x8, None, self._buf(tag + '.a', (H, W, 32), dt), [(3, 8)],
                        act_pre=ACT_LRELU02, pad=2)
-        self._resblock('aa2.align.conv1.2.conv1', 'aa2.align.conv1.2.conv2', a, out, self._buf(tag + '.t', (H, W, 32), dt),
+        self._resblock(aa + '.align.conv1.2.conv1', aa + '.align.conv1.2.conv2', a, out, self._buf(tag + '.t', (H, W, 32), dt),
                        ACT_LRELU02, ACT_LRELU02)
         return out
 
-    def _aa2(self, lr, ref8, idx, ref_feat, h, w, out):
-        """AlignedAttention scale=2 + AlignedConv2d (attention.py:131-159) -> out (2h,2w,C)."""
+    def _aligned_attention(self, aa, query_img, ref8, idx, value, out):
+        """AlignedAttention + AlignedConv2d (attention.py:131-159, alignment.py:39-100) -> out (2hq', 2wq', C) where
+        `query_img` (3, hq', wq') fp32 is the LR-side image (lr for aa2, lr_down for aa1), blocks are ks x ks pixels,
+        ks = module scale (aa2: 2, or 8 with flag_HD_in; aa1: 4 with flag_HD_in).  `ref8` is gathered on ITS OWN
+        block grid, as the reference does (RefVSR.py:127 passes the full-resolution reference image to aa1)."""
         C, dt = self.mid_channels, self.act_dtype
-        ks = self.aa2.scale
-        H2, W2 = 2 * h, 2 * w
-        warped = self._buf('aa2.wf', (H2, W2, C), dt)
-        self.ops.gather_blocks(ref_feat, idx, h, w, ks, warped)
-        wref8 = self._buf('aa2.wr', (H2, W2, 8), dt)
-        self.ops.gather_blocks(ref8, idx, h, w, ks, wref8)
-        q8 = self._buf('aa2.q8', (H2, W2, 8), dt)
-        self.ops.bicubic_up2_image(lr, q8)                       # alignment.py:41 (no clamp)
-        qf = self._align_conv1(q8, self._buf('aa2.qf', (H2, W2, 32), dt), 'aa2.c1q')
-        rf = self._align_conv1(wref8, self._buf('aa2.rf', (H2, W2, 32), dt), 'aa2.c1r')
+        ks = self.get_submodule(aa).scale
+        H2, W2 = 2 * query_img.shape[1], 2 * query_img.shape[2]
+        hq, wq = H2 // ks, W2 // ks
+        warped = self._buf(aa + '.wf', (H2, W2, C), dt)
+        self.ops.gather_blocks(value, idx, hq, wq, ks, warped)
+        wref8 = self._buf(aa + '.wr', (H2, W2, 8), dt)
+        self.ops.gather_blocks(ref8, idx, hq, wq, ks, wref8)
+        q8 = self._buf(aa + '.q8', (H2, W2, 8), dt)
+        self.ops.bicubic_up2_image(query_img, q8)                # alignment.py:41 (no clamp)
+        qf = self._align_conv1(aa, q8, self._buf(aa + '.qf', (H2, W2, 32), dt), aa + '.c1q')
+        rf = self._align_conv1(aa, wref8, self._buf(aa + '.rf', (H2, W2, 32), dt), aa + '.c1r')
         ha, wa = (H2 + 4 - 5) // ks + 1, (W2 + 4 - 5) // ks + 1
-        p0 = self._conv('aa2.align.p_conv.0', rf, qf, self._buf('aa2.p0', (ha, wa, 32), dt), [(32, 32), (32, 32)],
+        p0 = self._conv(aa + '.align.p_conv.0', rf, qf, self._buf(aa + '.p0', (ha, wa, 32), dt), [(32, 32), (32, 32)],
                         act_pre=ACT_LRELU02, stride=ks, pad=2)
-        p1 = self._resblock('aa2.align.p_conv.2.conv1', 'aa2.align.p_conv.2.conv2', p0, self._buf('aa2.p1', (ha, wa, 32), dt),
-                            self._buf('aa2.pt', (ha, wa, 32), dt), ACT_LRELU02, ACT_LRELU02)
-        affine = self._buf('aa2.aff', (ha, wa, 3), torch.float32)
-        self._conv('aa2.align.p_conv.4', p1, None, affine, [(32, 32)], act_post=ACT_CLAMP3, pad=0, bias_add=1.0)
+        p1 = self._resblock(aa + '.align.p_conv.2.conv1', aa + '.align.p_conv.2.conv2', p0, self._buf(aa + '.p1', (ha, wa, 32), dt),
+                            self._buf(aa + '.pt', (ha, wa, 32), dt), ACT_LRELU02, ACT_LRELU02)
+        affine = self._buf(aa + '.aff', (ha, wa, 3), torch.float32)
+        self._conv(aa + '.align.p_conv.4', p1, None, affine, [(32, 32)], act_post=ACT_CLAMP3, pad=0, bias_add=1.0)
         self.ops.aligned_sample(warped, affine, ks, out)
         return out
 
@@ -338,7 +362,7 @@ class Network(nn.Module):
         C, dt = self.mid_channels, self.act_dtype
         r = f'ring{self._b}'
         return {'conf': self._buf(f'{r}.conf.{slot}', (h, w), torch.float32),
-                'idx': self._buf(f'{r}.idx.{slot}', (h * w,), torch.int32),
+                'idx': self._buf(f'{r}.idx.{slot}', ((h // 4) * (w // 4) if self.flag_HD_in else h * w,), torch.int32),
                 'aligned': self._buf(f'{r}.al.{slot}', (h, w, C), dt),
                 'aligned_up': self._buf(f'{r}.alup.{slot}', (2 * h, 2 * w, C), dt),
                 'lr8': self._buf(f'{r}.lr8.{slot}', (h, w, 8), dt)}
@@ -352,8 +376,13 @@ class Network(nn.Module):
         fp = self._frame_slot(slot, h, w)
         self._feature_match(lr, ref, fp['conf'], fp['idx'])
         ref8, ref_feat, ref_feat_down = self._ref_features(ref)
-        self.ops.gather_blocks(ref_feat_down, fp['idx'], h, w, 1, fp['aligned'])   # aa1: scale 1, align=False
-        self._aa2(lr, ref8, fp['idx'], ref_feat, h, w, fp['aligned_up'])
+        if self.aa1.has_align:                                   # flag_HD_in: aa1 scale 4 with AlignedConv2d (RefVSR.py:37,125-127)
+            lr_down = self._buf('aa1.lrd', (3, h // 2, w // 2), torch.float32)
+            self.ops.resize_planes(lr, lr_down, 2.0, mode='bicubic', clamp01=True)
+            self._aligned_attention('aa1', lr_down, ref8, fp['idx'], ref_feat_down, fp['aligned'])
+        else:
+            self.ops.gather_blocks(ref_feat_down, fp['idx'], h, w, self.aa1.scale, fp['aligned'])   # aa1: scale 1, align=False
+        self._aligned_attention('aa2', lr, ref8, fp['idx'], ref_feat, fp['aligned_up'])
         self.ops.prep_image(lr, fp['lr8'])
         return fp
 

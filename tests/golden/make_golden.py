@@ -24,6 +24,11 @@ CASES = {
                                 ref_scale=2, frames=3, seed=12),
     'small_t7_24x32': dict(config='config_RefVSR_small_MFID', over=dict(num_blocks=1), T=7, h=24, w=32,
                            ref_scale=1, frames=5, seed=13),
+    # flag_HD_in ("8K") configs: VGG[0:7] matching at 1/4 resolution, matching_ksize 8, aa1 scale 4 / aa2 scale 8
+    'small8k_t3_32x48': dict(config='config_RefVSR_small_MFID_8K', over=dict(num_blocks=1, reset_branch=2), T=3, h=32, w=48,
+                             ref_scale=1, frames=5, seed=21),
+    'mfid8k_t5_48x64_noreset': dict(config='config_RefVSR_MFID_8K', over=dict(num_blocks=1), T=5, h=48, w=64,
+                                    ref_scale=1, frames=3, seed=22),
 }
 
 

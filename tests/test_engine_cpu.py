@@ -76,7 +76,8 @@ def test_state_dict_schema_matches_reference():
     (tests/golden/state_dict_keys.json); falls back to counts from SURVEY 8b."""
     from refvsr_b200 import SRNet, get_config
     counts = {'config_RefVSR_small_MFID': (428, 2492070), 'config_RefVSR_MFID': (476, 5717550),
-              'config_RefVSR_L1': (476, 5717550), 'config_RefVSR_small_L1': (428, 2492070)}
+              'config_RefVSR_L1': (476, 5717550), 'config_RefVSR_small_L1': (428, 2492070),
+              'config_RefVSR_small_MFID_8K': (444, 2657705), 'config_RefVSR_MFID_8K': (492, 5883185)}
     path = os.path.join(GOLDEN_DIR, 'state_dict_keys.json')
     ref_keys = json.load(open(path)) if os.path.isfile(path) else {}
     for name, (ntens, nparam) in counts.items():
@@ -148,7 +149,8 @@ def test_reset_branch_counter(oracle_ops):
 def test_unsupported_configs_fail_loudly():
     from refvsr_b200 import SRNet, get_config
     with pytest.raises(NotImplementedError):
-        SRNet(get_config('config_RefVSR_MFID_8K', device='cpu'))
+        SRNet(get_config('config_RefVSR_MFID', device='cpu', scale=2))          # the x2 models are not on this path
+    SRNet(get_config('config_RefVSR_MFID_8K', device='cpu', num_blocks=1))       # flag_HD_in is (schedule: HD goldens above)
 
 
 def test_product_has_no_cpu_fallback():
@@ -167,3 +169,17 @@ def test_product_has_no_cpu_fallback():
             if f.endswith('.py'):
                 src = open(os.path.join(dp, f)).read()
                 assert 'import oracle' not in src and 'from oracle' not in src, f
+
+
+def test_standalone_configs_match_the_reference_config_modules():
+    """refvsr_b200.config.get_config restates configs/config_RefVSR_*.py; fixture dumped from the reference by
+    tests/golden/make_config_values.py"""
+    import json
+    from refvsr_b200 import get_config
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'config_values.json')) as f:
+        ref = json.load(f)
+    assert len(ref) == 6
+    for name, fields in ref.items():
+        cfg = get_config(name, device='cpu')
+        for k, v in fields.items():
+            assert cfg[k] == v, (name, k, cfg[k], v)

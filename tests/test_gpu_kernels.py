@@ -232,6 +232,37 @@ def test_prep_image(cuda_ops, oracle_ops):
             close(got, exp, 1e-5, f'prep_image pool={pool}')
 
 
+@pytest.mark.parametrize('prec', ['fp32', 'fp16', 'bf16'])
+def test_maxpool2(cuda_ops, oracle_ops, prec):
+    """vgg19.features[4] of the flag_HD_in matching path (odd sizes drop the last row / column like nn.MaxPool2d)"""
+    dt = DT[prec]
+    for (H, W, C) in ((26, 38, 64), (9, 7, 8)):
+        x = rnd((H, W, C), 1, dt)
+        got, exp = both(oracle_ops.maxpool2, cuda_ops.maxpool2, (x,), (H // 2, W // 2, C), dt)
+        assert torch.equal(got.cpu(), exp), 'max of representable values is exact'
+
+
+def test_resize_planes(cuda_ops, oracle_ops):
+    """bicubic x4 (+clamp) of the relevance map, bicubic x0.5 (+clamp) of the LR frame, nearest x0.5 (attention.py:65-67,
+    96-98; RefVSR.py:125)"""
+    conf = torch.rand((1, 12, 17), generator=g(1)) * 1.2 - 0.1
+    got, exp = both(lambda s, o: oracle_ops.resize_planes(s, o, 0.25, 'bicubic', True),
+                    lambda s, o: cuda_ops.resize_planes(s, o, 0.25, 'bicubic', True), (conf,), (1, 48, 68), torch.float32)
+    close(got, exp, 1e-5, 'bicubic x4 clamp')
+    img = torch.rand((3, 26, 38), generator=g(2))
+    for clamp in (False, True):
+        got, exp = both(lambda s, o: oracle_ops.resize_planes(s, o, 2.0, 'bicubic', clamp),
+                        lambda s, o: cuda_ops.resize_planes(s, o, 2.0, 'bicubic', clamp), (img,), (3, 13, 19), torch.float32)
+        close(got, exp, 1e-5, f'bicubic x0.5 clamp={clamp}')
+    got, exp = both(lambda s, o: oracle_ops.resize_planes(s, o, 2.0, 'nearest'),
+                    lambda s, o: cuda_ops.resize_planes(s, o, 2.0, 'nearest'), (img,), (3, 13, 19), torch.float32)
+    assert torch.equal(got.cpu(), exp)
+    odd = torch.rand((3, 27, 39), generator=g(3))
+    got, exp = both(lambda s, o: oracle_ops.resize_planes(s, o, 2.0, 'nearest'),
+                    lambda s, o: cuda_ops.resize_planes(s, o, 2.0, 'nearest'), (odd,), (3, 13, 19), torch.float32)
+    assert torch.equal(got.cpu(), exp)
+
+
 def test_spynet_glue(cuda_ops, oracle_ops):
     img = torch.rand((3, 27, 45), generator=g(1))
     got, exp = both(oracle_ops.spynet_resize_norm, cuda_ops.spynet_resize_norm, (img,), (32, 64, 3), torch.float32)

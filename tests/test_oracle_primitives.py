@@ -117,3 +117,17 @@ def test_match_first_max_wins():
     lr_f[:] = 0.5
     conf, idx = O.match_argmax(lr_f, ref_f)
     assert (idx == 0).all() and torch.allclose(conf, torch.ones_like(conf), atol=1e-6)
+
+
+def test_hd_matching_primitives_match_aten():
+    """flag_HD_in path: nearest x0.5, 2x2 max pool, bicubic x4 / x0.5 (attention.py:65-67,31-40,96-98; RefVSR.py:125)"""
+    import torch.nn.functional as F
+    from oracle import refvsr_oracle as O
+    gen = torch.Generator().manual_seed(3)
+    for shape in ((1, 3, 26, 38), (2, 5, 27, 39)):
+        x = torch.rand(shape, generator=gen)
+        assert torch.equal(O.nearest_down2(x), F.interpolate(x, scale_factor=0.5, mode='nearest'))
+        assert torch.equal(O.maxpool2(x), F.max_pool2d(x, 2, 2))
+        for sc in (0.5, 4):
+            ref = F.interpolate(x, scale_factor=sc, mode='bicubic', align_corners=False)
+            assert (O.bicubic(x, sc) - ref).abs().max() < 1e-6
