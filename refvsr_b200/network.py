@@ -527,6 +527,10 @@ class Network(nn.Module):
             raise ValueError('reference frames must have even height/width (2x2 avg-pool and 2x2 block '
                              'gather, attention.py:51,142-144; odd sizes take the reference\'s reflection-'
                              'padded unfold path, which is not implemented)')
+        if self.flag_HD_in and (h % 4 or w % 4 or refs.size(3) % 8 or refs.size(4) % 8):
+            raise ValueError('flag_HD_in: LR height/width must be multiples of 4 and Ref height/width multiples of 8 '
+                             '(4x4 / 8x8 alignment blocks on the 1/4-resolution matching grid, attention.py:142-154); '
+                             f'got LR {h}x{w}, Ref {refs.size(3)}x{refs.size(4)}')
         self._device = lrs.device
 
         caller_first = bool(is_first_frame)

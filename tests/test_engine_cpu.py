@@ -134,6 +134,13 @@ def test_forward_contract_and_errors(oracle_ops):
     assert set(d) == {'x', 'ref'} and d['x'].shape == (1, 3, 3, 16, 16)
 
 
+def test_hd_input_size_contract(oracle_ops):
+    spec, cfg, net, lrs, refs, golden = build_case('small8k_t3_32x48', 'cpu', ops=oracle_ops, b200_precision='fp32')
+    x = torch.rand(1, 3, 3, 30, 48)
+    with pytest.raises(ValueError, match='flag_HD_in'):
+        net(x, x, True)
+
+
 def test_reset_branch_counter(oracle_ops):
     """forced first-frame windows at call indices 0, reset_branch, 2*reset_branch, ... (RefVSR.py:168-170)"""
     from refvsr_b200.synth import sliding_windows
