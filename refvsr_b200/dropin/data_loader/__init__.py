@@ -10,9 +10,9 @@ import os
 import sys
 
 _here = os.path.dirname(os.path.abspath(__file__))
-for _p in sys.path:
-    _cand = os.path.join(_p, 'data_loader')
-    if _p and os.path.isdir(_cand) and os.path.abspath(_cand) != _here and os.path.isfile(os.path.join(_cand, 'datasets.py')):
+for _p in list(sys.path) + [os.getcwd()]:
+    _cand = os.path.join(_p or os.getcwd(), 'data_loader')      # '' on sys.path = the current directory
+    if os.path.isdir(_cand) and os.path.abspath(_cand) != _here and os.path.isfile(os.path.join(_cand, 'datasets.py')):
         __path__.append(_cand)          # noqa: F821  (package attribute): the reference's modules resolve from here
         REFERENCE_DIR = _cand
         break
