@@ -213,6 +213,15 @@ int rv_conf_pair(const float* a, const float* b, int h, int w, int up2, void* ou
 int rv_conf_max(const float* a, const float* b, float* out, int n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Guard of the sliding-window reuse (no reference counterpart: the reference silently ASSUMES that consecutive calls slide
+ * the window by one frame when it reuses forward_*_prev, RefVSR.py:256-260; this implementation also reuses per-frame
+ * products, so it checks).  Compares n <= 16 (a[i], b[i], nbytes[i]) DEVICE buffer pairs; the pointer / size arrays
+ * themselves are HOST arrays.  *flag (device int32, zeroed by the caller) becomes non-zero iff any pair differs.
+ * ------------------------------------------------------------------------------------------------ */
+int rv_frames_differ(const void* const* a, const void* const* b, const uint64_t* nbytes, int n, int32_t* flag,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Reconstruction tail (RefVSR.py:118,288,297): out = conv_last_out + clamp(bicubic_x4(lr),0,1),
  * optionally clamped to [0,1]; written NCHW fp32 (3, 4h, 4w).  x (4h,4w,xc) is conv_last's output.
  * ------------------------------------------------------------------------------------------------ */

@@ -185,6 +185,9 @@ class OracleOps:
     def conf_max(self, a, b, out):
         out.copy_(torch.maximum(a, b))
 
+    def frames_differ(self, pairs, flag):
+        flag.fill_(0 if all(torch.equal(a, b) for a, b in pairs) else 1)
+
     # ---- tail ----
     def reconstruct(self, x, lr, scale, clamp01, out):
         base = O.bicubic(lr.float().unsqueeze(0), scale).clamp(0, 1)

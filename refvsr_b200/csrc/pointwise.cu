@@ -612,12 +612,53 @@ __global__ void reconstruct_kernel(const T* __restrict__ x, int xc, const float*
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// rv_frames_differ : guard of the sliding-window reuse cache (network.py).  Up to 16 (a, b, bytes) buffer pairs are
+// compared in one launch; *flag |= 1 as soon as any pair differs.  blockIdx.y = pair.
+// ---------------------------------------------------------------------------------------------
+struct CmpPairs {
+  const void* a[16];
+  const void* b[16];
+  unsigned long long nbytes[16];
+};
+
+template <typename V>
+__global__ void frames_differ_kernel(const CmpPairs P, int* __restrict__ flag) {
+  const V* a = reinterpret_cast<const V*>(P.a[blockIdx.y]);
+  const V* b = reinterpret_cast<const V*>(P.b[blockIdx.y]);
+  const size_t n = (size_t)(P.nbytes[blockIdx.y] / sizeof(V));
+  bool diff = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const V x = a[i], y = b[i];
+    if constexpr (sizeof(V) == 16) diff |= (x.x != y.x) | (x.y != y.y) | (x.z != y.z) | (x.w != y.w);
+    else diff |= (x != y);
+  }
+  if (__any_sync(0xffffffffu, diff) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 }  // namespace rv
 
 // =================================================================================================
 // C ABI
 // =================================================================================================
 using namespace rv;
+
+extern "C" int rv_frames_differ(const void* const* a, const void* const* b, const uint64_t* nbytes, int n, int32_t* flag,
+                                void* stream) {
+  RV_REQUIRE(a && b && nbytes && flag && n > 0 && n <= 16, "rv_frames_differ: 1..16 buffer pairs (got %d)", n);
+  CmpPairs P;
+  bool vec = true;
+  for (int i = 0; i < n; ++i) {
+    RV_REQUIRE(a[i] && b[i] && nbytes[i] % 4 == 0, "rv_frames_differ: null buffer or size not a multiple of 4 (pair %d)", i);
+    P.a[i] = a[i]; P.b[i] = b[i]; P.nbytes[i] = nbytes[i];
+    vec = vec && ((uintptr_t)a[i] % 16 == 0) && ((uintptr_t)b[i] % 16 == 0) && (nbytes[i] % 16 == 0);
+  }
+  dim3 grid(64, n);
+  if (vec) frames_differ_kernel<uint4><<<grid, 256, 0, (cudaStream_t)stream>>>(P, flag);
+  else frames_differ_kernel<uint32_t><<<grid, 256, 0, (cudaStream_t)stream>>>(P, flag);
+  RV_LAUNCH_CHECK("frames_differ");
+  return RV_OK;
+}
 
 extern "C" int rv_prep_image(const float* src, int H, int W, const float* mat12_host, int pool2,
                              void* out, int out_c, int out_dtype, void* stream) {

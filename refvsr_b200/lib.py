@@ -68,6 +68,7 @@ SIGNATURES = {
     'rv_bicubic_up2_image': (_I, [_P, _I, _I, _P, _I, _I, _P]),
     'rv_conf_pair': (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _P]),
     'rv_conf_max': (_I, [_P, _P, _P, _I, _P]),
+    'rv_frames_differ': (_I, [_P, _P, _P, _I, _P, _P]),
     'rv_reconstruct': (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _P, _P]),
 }
 
@@ -280,6 +281,19 @@ class CudaOps:
     def conf_max(self, a, b, out):
         _chk_dev(a, b, out)
         _check(self.lib, self.lib.rv_conf_max(_ptr(a), _ptr(b), _ptr(out), a.numel(), self._stream()), 'rv_conf_max')
+
+    def frames_differ(self, pairs, flag):
+        """pairs: [(a, b)] contiguous same-size CUDA tensors; flag (1,) int32, zeroed here, set non-zero iff any pair differs"""
+        n = len(pairs)
+        assert 0 < n <= 16
+        for a, b in pairs:
+            _chk_dev(a, b)
+            assert a.numel() * a.element_size() == b.numel() * b.element_size() and a.dtype == b.dtype
+        pa = (C.c_void_p * n)(*[a.data_ptr() for a, _ in pairs])
+        pb = (C.c_void_p * n)(*[b.data_ptr() for _, b in pairs])
+        nb = (C.c_uint64 * n)(*[a.numel() * a.element_size() for a, _ in pairs])
+        flag.zero_()
+        _check(self.lib, self.lib.rv_frames_differ(pa, pb, nb, n, _ptr(flag), self._stream()), 'rv_frames_differ')
 
     # -- tail -------------------------------------------------------------------------------------
     def reconstruct(self, x, lr, scale, clamp01, out):

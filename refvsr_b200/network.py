@@ -73,6 +73,16 @@ class Network(nn.Module):
         self.match_mode = _cget(config, 'b200_match', 'split' if prec == 'fp32' else 'single')
         self.prefer_tc = bool(_cget(config, 'b200_tensor_cores', True))
         self.reuse = bool(_cget(config, 'b200_reuse', True))
+        # the reuse cache is only valid when consecutive calls slide the window by exactly one frame (what the reference's
+        # own eval loop does, data_loader/datasets.py:222-245).  'sync' (default): every non-first call compares the t-1
+        # overlapping LR / Ref frames with the staged copies on the device (one launch, ~20 MB read) and reads the verdict
+        # back before choosing the schedule - a caller that does NOT slide gets a full recompute, i.e. exactly what the
+        # reference would compute for that call.  'async': same check, verdict read at the NEXT call -> RuntimeError
+        # (no host sync on the hot path).  'off': trust the caller (round-1 behaviour).
+        self.reuse_check = _cget(config, 'b200_reuse_check', 'sync')
+        if self.reuse_check not in ('sync', 'async', 'off'):
+            raise ValueError("b200_reuse_check must be 'sync', 'async' or 'off'")
+        self.reuse_fallbacks = 0      # calls that violated the sliding contract and were recomputed from scratch
         self.use_graphs = bool(_cget(config, 'b200_cuda_graphs', True))
         # fused residual-block kernel: validated, but not faster than two conv launches yet (MMA-instruction bound,
         # profiles/r01_conv_knockout.md) -> opt-in
@@ -532,6 +542,10 @@ class Network(nn.Module):
                              '(4x4 / 8x8 alignment blocks on the 1/4-resolution matching grid, attention.py:142-154); '
                              f'got LR {h}x{w}, Ref {refs.size(3)}x{refs.size(4)}')
         self._device = lrs.device
+        if is_train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # trainers/trainer.py:159-172 would call loss.backward() on the result: fail here, with a clear message
+            raise NotImplementedError('refvsr_b200 is inference only: forward(is_train=True) builds no autograd graph '
+                                      '(call it under torch.no_grad() for a training-mode forward without gradients)')
 
         caller_first = bool(is_first_frame)
         if not is_train:                                                     # RefVSR.py:168-170
@@ -569,6 +583,8 @@ class Network(nn.Module):
         st = self._state.get(b)
         shape = (t, h, w, hr, wr)
         fresh = (st is None or caller_first or not self.reuse or is_train or st.get('shape') != shape)
+        if not fresh and self.reuse_check != 'off':
+            fresh = not self._window_slid_by_one(st, lrs, refs, t, h, w, hr, wr)
         if fresh:
             st = {'a0': 0, 'pyr': set(), 'fw': set(), 'bw': set(), 'frame': set(), 'staged': set(),
                   'has_prev': bool(st and st.get('has_prev')) and st.get('shape') == shape, 'shape': shape}
@@ -619,6 +635,41 @@ class Network(nn.Module):
             out = out_static.clone()
         st['has_prev'] = True
         return out, vis
+
+    def _window_slid_by_one(self, st, lrs, refs, t, h, w, hr, wr):
+        """Reuse guard: frames 0..t-2 of this call must be frames 1..t-1 of the previous one, i.e. equal to the staged ring
+        slots a0+1 .. a0+t-1 (bitwise: the slots are fp32 copies of what the caller passed).  Returns False when the
+        cached per-frame products must not be reused for this call."""
+        flag = self._buf(f'reuse.flag{self._b}', (1,), torch.int32)
+        if self.reuse_check == 'async' and st.get('check_pending'):
+            st['check_pending'] = False
+            if int(flag.item()):
+                self.reuse_fallbacks += 1
+                raise RuntimeError('refvsr_b200: the previous call did not slide the window by one frame '
+                                   '(is_first_frame=False with different overlapping frames); its output reused stale '
+                                   "per-frame products.  Pass is_first_frame=True for a new clip or set b200_reuse_check='sync'")
+        a1 = st['a0'] + 1
+        lr32 = lrs if (lrs.dtype == torch.float32 and lrs.is_contiguous()) else lrs.float().contiguous()
+        rf32 = refs if (refs.dtype == torch.float32 and refs.is_contiguous()) else refs.float().contiguous()
+        pairs = []
+        for j in range(t - 1):
+            pairs.append((lr32[j], self._ring('lr32', a1 + j, t, (3, h, w))))
+            pairs.append((rf32[j], self._ring('ref32', a1 + j, t, (3, hr, wr))))
+        for i in range(0, len(pairs), 16):
+            chunk = pairs[i:i + 16]
+            if i == 0:
+                self.ops.frames_differ(chunk, flag)
+            else:
+                flag2 = self._buf(f'reuse.flag{self._b}.{i}', (1,), torch.int32)
+                self.ops.frames_differ(chunk, flag2)
+                flag.bitwise_or_(flag2)
+        if self.reuse_check == 'async':
+            st['check_pending'] = True
+            return True
+        if int(flag.item()):          # one small host sync per call; the staged frames of the previous call are the reference
+            self.reuse_fallbacks += 1
+            return False
+        return True
 
     def _run_window(self, b, st, a0, t, h, w, hr, wr, work, is_first_frame, range_start, is_log, is_train):
         """All kernel launches of one window.  Reads / writes static buffers only (graph-capturable)."""

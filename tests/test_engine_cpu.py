@@ -124,7 +124,8 @@ def test_forward_contract_and_errors(oracle_ops):
     assert 'vis' in outs and 'BW_LR_next_warp' in outs['vis'] and outs['vis']['BW_LR_next_warp'].shape == (1, 3, 32, 48)
     # training-mode call: no clamp, frame counter untouched (RefVSR.py:292-297)
     n0 = net.Network.frame_itr_num
-    o = net(wl, wr, True, False, True)['result']
+    with torch.no_grad():                # autograd-enabled training forwards raise (inference-only product)
+        o = net(wl, wr, True, False, True)["result"]
     assert net.Network.frame_itr_num == n0 and o.shape == (1, 3, 128, 192)
     # batch of 2 == two independent streams
     o2 = net(torch.cat([wl, wl], 0), torch.cat([wr, wr], 0), True)['result']
@@ -190,3 +191,38 @@ def test_standalone_configs_match_the_reference_config_modules():
         cfg = get_config(name, device='cpu')
         for k, v in fields.items():
             assert cfg[k] == v, (name, k, cfg[k], v)
+
+
+def test_reuse_guard_non_sliding_caller(oracle_ops):
+    """ADVICE r1 (medium) / VERDICT r1 item 8: a caller that passes is_first_frame=False but does NOT slide the window by
+    one frame must get what the reference computes for those calls (sync guard: full recompute), or a loud error (async
+    guard) - never silently stale products."""
+    from oracle.refvsr_oracle import OracleRefVSR
+    from refvsr_b200.synth import sliding_windows
+    spec, cfg, net, lrs, refs, golden = build_case('small_t7_24x32', 'cpu', ops=oracle_ops, b200_precision='fp32')
+    orc = OracleRefVSR(cfg, net.state_dict())
+    wins = list(sliding_windows(lrs, refs, spec['T']))
+    order = [0, 2, 3, 1]                      # 0 -> 2 jumps by two frames, 3 slides, 1 jumps backwards
+    for n, k in enumerate(order):
+        _, wl, wr, _ = wins[k]
+        out = net(wl, wr, n == 0, False, False)['result']
+        exp = orc.forward(wl, wr, n == 0)
+        assert psnr(out[0], exp[0]) > 95.0, f'call {n} (window {k})'
+    assert net.Network.reuse_fallbacks == 2
+    # async guard: the violation surfaces as an exception on the following call
+    spec, cfg, net, lrs, refs, golden = build_case('small_t7_24x32', 'cpu', ops=oracle_ops, b200_precision='fp32',
+                                                   b200_reuse_check='async')
+    net(wins[0][1], wins[0][2], True)
+    net(wins[2][1], wins[2][2], False)        # violation: not detected yet
+    with pytest.raises(RuntimeError, match='did not slide'):
+        net(wins[3][1], wins[3][2], False)
+
+
+def test_training_mode_forward_fails_loudly(oracle_ops):
+    """is_train=True with autograd enabled would silently return a tensor without grad_fn"""
+    spec, cfg, net, lrs, refs, golden = build_case('small_t3_32x48', 'cpu', ops=oracle_ops, b200_precision='fp32')
+    wl, wr = lrs[[0, 0, 1]].unsqueeze(0), refs[[0, 0, 1]].unsqueeze(0)
+    with pytest.raises(NotImplementedError, match='inference only'):
+        net(wl, wr, True, False, True)
+    with torch.no_grad():
+        assert net(wl, wr, True, False, True)['result'].shape[1] == 3
