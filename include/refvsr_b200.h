@@ -120,6 +120,37 @@ typedef struct rv_resblock_desc {
 
 int rv_resblock(const rv_resblock_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * rv_conv_chain - a CHAIN of 3x3 C->C convolutions (+ bias, activation, residual, activation) over a small set of NHWC
+ * f16/bf16 buffers of identical geometry, executed by ONE persistent tcgen05 launch with per-tile dependencies between
+ * layers and a TMA-store epilogue (refvsr_b200/csrc/conv_chain.cu).  Replaces, launch for launch,
+ *   make_layer(ResidualBlockNoBN, num_blocks)  (mmedit/models/common/sr_backbone_utils.py:26-39,85-97; RefVSR.py:346-349)
+ *   ResList: N x ResBlock + conv_tail + skip    (RefVSR_/common.py:25-39,64-82; RefVSR.py:48-60,233-234)
+ * Layer l computes  buf[dst] = act_post( act_pre( conv3x3(buf[src]) + bias ) + buf[res] )   (res < 0: no residual), zero
+ * padding 1.  dst must differ from src.  wpack = the layout-1 tensor-core weight image of rv_conv2d ([9 taps][nb][64]
+ * 16-bit, SWIZZLE_128B byte image), bias = nb floats (zero beyond cout).  All buffers: (H, W, C), C % 8 == 0, C <= 48.
+ * `flags` is device scratch of >= ceil(H/16) * ceil(W/8) int32 (zeroed by the call, on `stream`).
+ * Results are bit-identical to the same layers issued one by one through rv_conv2d.
+ * ------------------------------------------------------------------------------------------------ */
+#define RV_CHAIN_MAX_LAYERS 64
+#define RV_CHAIN_MAX_BUFFERS 6
+typedef struct {
+  const void* wpack;
+  const float* bias;
+  int32_t src, res, dst;
+  int32_t act_pre, act_post; /* RV_ACT_NONE / RELU / LRELU01 / LRELU02 */
+} rv_chain_layer;
+typedef struct {
+  void* buf[RV_CHAIN_MAX_BUFFERS];
+  int32_t nbuf;
+  int32_t H, W, C, dtype; /* C = allocated channels (row pitch) of every buffer */
+  int32_t nb;             /* rows of the weight image (16 / 32 / 48), >= C */
+  const rv_chain_layer* layers; /* HOST array */
+  int32_t nlayers;
+  int32_t* flags;
+} rv_conv_chain_desc;
+int rv_conv_chain(const rv_conv_chain_desc* d, void* stream);
+
 /* space-to-depth by 2: out[(Y,X)][(ry*2+rx)*C + c] = src[(2Y+ry, 2X+rx)][c].  Turns the two stride-2
  * convolutions of the path (ref_encoder2.0.0, RefVSR.py:45; aa2.align.p_conv.0, alignment.py:21) into
  * stride-1 3x3 convolutions over 4C channels (weights re-indexed by packing.s2d_weights), so they run on

@@ -185,6 +185,18 @@ class OracleOps:
     def conf_max(self, a, b, out):
         out.copy_(torch.maximum(a, b))
 
+    def pack_chain(self, name, weight, bias, alloc, act_dtype, device):
+        c = weight.shape[0]
+        return types.SimpleNamespace(name=name, nb=(alloc + 15) // 16 * 16, weight=weight.detach().float().cpu(),
+                                     bias=bias.detach().float().cpu(), srcs=[(c, alloc)], stride=1, pad=1, cout=c,
+                                     alloc0=alloc, alloc1=0)
+
+    def conv_chain(self, bufs, layers, flags):
+        """the chain's contract: exactly the layers, one after the other"""
+        for pk, src, res, dst, a0, a1 in layers:
+            assert dst != src
+            self.conv2d(pk, bufs[src], None, bufs[dst], res=bufs[res] if res >= 0 else None, act_pre=a0, act_post=a1)
+
     def frames_differ(self, pairs, flag):
         flag.fill_(0 if all(torch.equal(a, b) for a, b in pairs) else 1)
 

@@ -44,6 +44,19 @@ class rv_resblock_desc(C.Structure):
     ]
 
 
+class rv_chain_layer(C.Structure):
+    _fields_ = [('wpack', C.c_void_p), ('bias', C.c_void_p), ('src', C.c_int32), ('res', C.c_int32), ('dst', C.c_int32),
+                ('act_pre', C.c_int32), ('act_post', C.c_int32)]
+
+
+class rv_conv_chain_desc(C.Structure):
+    _fields_ = [('buf', C.c_void_p * 6), ('nbuf', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C', C.c_int32),
+                ('dtype', C.c_int32), ('nb', C.c_int32), ('layers', C.POINTER(rv_chain_layer)), ('nlayers', C.c_int32),
+                ('flags', C.c_void_p)]
+
+
+CHAIN_MAX_LAYERS, CHAIN_MAX_BUFFERS = 64, 6
+
 # name -> (restype, argtypes); mirrors include/refvsr_b200.h one to one (tests check the export list)
 _P, _I, _F = C.c_void_p, C.c_int, C.c_float
 SIGNATURES = {
@@ -52,6 +65,7 @@ SIGNATURES = {
     'rv_launch_count': (C.c_uint64, []),
     'rv_conv2d': (_I, [C.POINTER(rv_conv_desc), _P]),
     'rv_resblock': (_I, [C.POINTER(rv_resblock_desc), _P]),
+    'rv_conv_chain': (_I, [C.POINTER(rv_conv_chain_desc), _P]),
     'rv_space_to_depth2': (_I, [_P, _I, _I, _I, _I, _P, _P]),
     'rv_prep_image': (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _P]),
     'rv_spynet_resize_norm': (_I, [_P, _I, _I, _P, _I, _I, _P]),
@@ -175,6 +189,29 @@ class CudaOps:
         d.cout, d.nb, d.act_mid, d.act_post = rb.cout, rb.nb, act_mid, act_post
         d.out, d.out_cs = out.data_ptr(), out.shape[2]
         _check(self.lib, self.lib.rv_resblock(C.byref(d), self._stream()), f'rv_resblock[{rb.name}]')
+
+    def conv_chain(self, bufs, layers, flags):
+        """bufs: list of (H, W, C) tensors of one dtype / geometry; layers: [(packing.PackedChainLayer, src, res, dst, act_pre,
+        act_post)] with buffer indices (res = -1: none); flags: int32 scratch with >= ceil(H/16)*ceil(W/8) entries.
+        Launches ceil(len(layers) / 64) persistent kernels (rv_conv_chain)."""
+        _chk_dev(*bufs)
+        H, W, Cc = bufs[0].shape
+        assert all(tuple(b.shape) == (H, W, Cc) and b.dtype == bufs[0].dtype for b in bufs) and len(bufs) <= CHAIN_MAX_BUFFERS
+        assert flags.dtype == torch.int32 and flags.numel() >= ((H + 15) // 16) * ((W + 7) // 8)
+        nb = layers[0][0].nb
+        for i in range(0, len(layers), CHAIN_MAX_LAYERS):
+            part = layers[i:i + CHAIN_MAX_LAYERS]
+            arr = (rv_chain_layer * len(part))()
+            for j, (pk, src, res, dst, a0, a1) in enumerate(part):
+                assert pk.nb == nb
+                arr[j].wpack, arr[j].bias = pk.wpack.data_ptr(), pk.bias.data_ptr()
+                arr[j].src, arr[j].res, arr[j].dst, arr[j].act_pre, arr[j].act_post = src, res, dst, a0, a1
+            d = rv_conv_chain_desc()
+            for b, t in enumerate(bufs):
+                d.buf[b] = t.data_ptr()
+            d.nbuf, d.H, d.W, d.C, d.dtype, d.nb = len(bufs), H, W, Cc, DTYPE_CODE[bufs[0].dtype], nb
+            d.layers, d.nlayers, d.flags = arr, len(part), flags.data_ptr()
+            _check(self.lib, self.lib.rv_conv_chain(C.byref(d), self._stream()), 'rv_conv_chain')
 
     def space_to_depth2(self, src, out):
         _chk_dev(src, out)

@@ -18,6 +18,7 @@ confined to *how* results are obtained, never to what they are:
   * no gc.collect()/empty_cache() (RefVSR.py:206-208), no host synchronisation inside forward.
 """
 import collections
+import os
 
 import torch
 import torch.nn as nn
@@ -87,6 +88,9 @@ class Network(nn.Module):
         # fused residual-block kernel: validated, but not faster than two conv launches yet (MMA-instruction bound,
         # profiles/r01_conv_knockout.md) -> opt-in
         self.fuse_resblocks = bool(_cget(config, 'b200_fuse_resblocks', False))
+        # cross-layer persistent chain kernel (rv_conv_chain): the 60-conv propagation trunks and the ResList decoders as ONE
+        # launch each, bit-identical to the per-layer path (csrc/conv_chain.cu)
+        self.use_chain = bool(_cget(config, 'b200_conv_chain', True)) and not os.environ.get('REFVSR_NO_CHAIN')   # (env: A/B runs)
         self._bufs = {}
         self._device = torch.device('cpu')
         self._b = 0
@@ -191,12 +195,43 @@ class Network(nn.Module):
         self._conv(conv2, tmp, None, out, [(C, C)], res=x, act_post=act_post)
         return out
 
+    def _chain_layer(self, name, C):
+        key = ('chain', name)
+        hit = self._packed.get(key)
+        if hit is None:
+            mod = self.get_submodule(name)
+            pack = self.ops.pack_chain if hasattr(self.ops, 'pack_chain') else packing.pack_chain
+            hit = pack(name, mod.weight, mod.bias, C, self.act_dtype, self._device)
+            self._packed[key] = hit
+        return hit
+
+    def _chain_ok(self, names, C):
+        return (self.use_chain and self.prefer_tc and not self.fuse_resblocks and hasattr(self.ops, 'conv_chain')
+                and all(packing.chain_ok(self.get_submodule(n).weight, C, self.act_dtype) for n in names))
+
+    def _run_chain(self, bufs, layers):
+        H, W = bufs[0].shape[0], bufs[0].shape[1]
+        flags = self._buf('chain.flags', (((H + 15) // 16) * ((W + 7) // 8),), torch.int32)
+        self.ops.conv_chain(bufs, layers, flags)
+
     def _reslist(self, prefix, n, x, out, tag):
         """ResList (RefVSR_/common.py:64-82): n x [x + conv2(lrelu0.2(conv1(x)))], conv_tail, + input."""
         C = x.shape[2]
         H, W = x.shape[0], x.shape[1]
         t = self._buf(tag + '.t', (H, W, C), x.dtype)
         s = [self._buf(tag + '.s0', (H, W, C), x.dtype), self._buf(tag + '.s1', (H, W, C), x.dtype)]
+        names = [f'{prefix}.RBs.{i}.conv{j}' for i in range(n) for j in (1, 2)] + [f'{prefix}.conv_tail']
+        if self._chain_ok(names, C):
+            bufs = [x, s[0], s[1], t, out]              # buffer indices 0..4
+            layers, cur = [], 0
+            for i in range(n):
+                nxt = 1 + (i % 2)
+                layers.append((self._chain_layer(f'{prefix}.RBs.{i}.conv1', C), cur, -1, 3, ACT_LRELU02, ACT_NONE))
+                layers.append((self._chain_layer(f'{prefix}.RBs.{i}.conv2', C), 3, cur, nxt, ACT_NONE, ACT_NONE))
+                cur = nxt
+            layers.append((self._chain_layer(f'{prefix}.conv_tail', C), cur, 0, 4, ACT_NONE, ACT_NONE))
+            self._run_chain(bufs, layers)
+            return out
         cur = x
         for i in range(n):
             nxt = s[i % 2]
@@ -214,6 +249,17 @@ class Network(nn.Module):
         s = [self._buf(tag + '.s0', (H, W, C), feat.dtype), self._buf(tag + '.s1', (H, W, C), feat.dtype)]
         cur = self._conv(f'{prefix}.main.0', lr8, feat, out if nblk == 0 else s[0], [(3, 8), (C, C)],
                          act_pre=ACT_LRELU01)
+        names = [f'{prefix}.main.2.{i}.conv{j}' for i in range(nblk) for j in (1, 2)]
+        if nblk > 0 and self._chain_ok(names, C):
+            bufs = [s[0], s[1], t, out]                 # buffer indices 0..3
+            layers, ci = [], 0
+            for i in range(nblk):
+                ni = 3 if i == nblk - 1 else 1 - ci
+                layers.append((self._chain_layer(f'{prefix}.main.2.{i}.conv1', C), ci, -1, 2, ACT_RELU, ACT_NONE))
+                layers.append((self._chain_layer(f'{prefix}.main.2.{i}.conv2', C), 2, ci, ni, ACT_NONE, ACT_NONE))
+                ci = ni
+            self._run_chain(bufs, layers)
+            return out
         for i in range(nblk):
             nxt = out if i == nblk - 1 else (s[1] if cur is s[0] else s[0])
             self._resblock(f'{prefix}.main.2.{i}.conv1', f'{prefix}.main.2.{i}.conv2', cur, nxt, t, ACT_RELU)

@@ -232,3 +232,31 @@ def pack_resblock(name, w1, b1, w2, b2, alloc, act_dtype, device):
     p2 = pack_tc(w2.detach(), [(c, alloc)], act_dtype, nb, layout=1).to(device)
     return PackedResBlock(name, c, alloc, nb, p1, b1.detach().float().to(device).contiguous(), p2,
                           b2.detach().float().to(device).contiguous())
+
+
+@dataclass
+class PackedChainLayer:
+    name: str
+    nb: int
+    wpack: torch.Tensor      # [1][1][9][nb][64] layout-1 image
+    bias: torch.Tensor       # nb floats, zero beyond cout
+
+
+def chain_nb(alloc):
+    return (alloc + 15) // 16 * 16
+
+
+def chain_ok(weight, alloc, act_dtype):
+    """can this conv be a layer of rv_conv_chain?  3x3, C -> C, 16-bit activations, C <= 48 allocated channels"""
+    c = weight.shape[0]
+    return (act_dtype in (torch.float16, torch.bfloat16) and tuple(weight.shape) == (c, c, 3, 3) and alloc % 8 == 0
+            and c <= alloc <= 48)
+
+
+def pack_chain(name, weight, bias, alloc, act_dtype, device):
+    c = weight.shape[0]
+    nb = chain_nb(alloc)
+    wp = pack_tc(weight.detach(), [(c, alloc)], act_dtype, nb, layout=1).to(device)
+    b = torch.zeros(nb, dtype=torch.float32)
+    b[:c] = bias.detach().float().cpu()
+    return PackedChainLayer(name, nb, wp, b.to(device).contiguous())

@@ -226,3 +226,31 @@ def test_training_mode_forward_fails_loudly(oracle_ops):
         net(wl, wr, True, False, True)
     with torch.no_grad():
         assert net(wl, wr, True, False, True)['result'].shape[1] == 3
+
+
+def test_conv_chain_schedule_is_the_per_layer_schedule(oracle_ops, monkeypatch):
+    """network.py routes the propagation trunks and the ResList decoders through ops.conv_chain (one persistent launch on
+    the GPU); the buffer / residual indexing of those chains must describe exactly the per-layer network"""
+    import refvsr_b200.packing as packing
+    from refvsr_b200.synth import sliding_windows
+    res = {}
+    for chain in (False, True):
+        spec, cfg, net, lrs, refs, golden = build_case('small_t3_32x48', 'cpu', ops=oracle_ops, b200_precision='fp32',
+                                                       b200_conv_chain=chain)
+        calls = {'n': 0, 'layers': 0}
+        orig = oracle_ops.conv_chain
+
+        def counting(bufs, layers, flags, _o=orig, _c=calls):
+            _c['n'] += 1
+            _c['layers'] += len(layers)
+            return _o(bufs, layers, flags)
+        monkeypatch.setattr(oracle_ops, 'conv_chain', counting)
+        monkeypatch.setattr(packing, 'chain_ok', lambda w, alloc, dt: tuple(w.shape[1:]) == (w.shape[0], 3, 3) and alloc <= 48)
+        res[chain] = [net(wl, wr, first)['result'] for k, wl, wr, first in sliding_windows(lrs, refs, spec['T'])]
+        monkeypatch.undo()
+        if chain:   # per propagation step: trunk (2 x 3 blocks) + feat_decoder (17) + feat_decoder2 (9); res1/res2 per frame; BWFW per window
+            assert calls['n'] > 20 and calls['layers'] > 300, calls
+        else:
+            assert calls['n'] == 0
+    for a, b in zip(res[True], res[False]):
+        assert torch.equal(a, b)

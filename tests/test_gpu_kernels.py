@@ -430,3 +430,85 @@ def test_errors_are_python_exceptions(cuda_ops):
     with pytest.raises(AssertionError):
         cuda_ops.conv2d(lc, torch.zeros((8, 8, 40), dtype=torch.float16, device='cuda'), None,
                         torch.zeros((8, 8, 48), dtype=torch.float16, device='cuda'))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# rv_conv_chain: persistent cross-layer kernel (conv_chain.cu) == the same layers launched one by one, bit for bit
+# ---------------------------------------------------------------------------------------------------------------------
+def _chain_case(cuda_ops, C, H, W, dt, kind, nblk, seed=0):
+    from refvsr_b200 import packing
+    from refvsr_b200.lib import ACT_LRELU02, ACT_NONE, ACT_RELU
+    g = torch.Generator().manual_seed(seed)
+    mk = lambda: torch.randn((H, W, C), generator=g).to(dt).cuda()
+    nconv = 2 * nblk + (1 if kind == 'reslist' else 0)
+    ws = [(torch.rand((C, C, 3, 3), generator=g) - 0.5) * (0.35 if i % 2 == 0 else 0.1) for i in range(nconv)]
+    bs = [(torch.rand((C,), generator=g) - 0.5) * 0.1 for _ in range(nconv)]
+    chain_l = [packing.pack_chain(f'c{i}', ws[i], bs[i], C, dt, 'cuda') for i in range(nconv)]
+    # per-layer twin: layout 3 = the single-box image WITHOUT the kx-folded mode (whose fp32 summation order differs)
+    conv_l = [packing.pack_conv(f'c{i}', ws[i], bs[i], [(C, C)], 1, 1, dt, 'cuda', True, tc_layout=3) for i in range(nconv)]
+    x = mk()
+    if kind == 'trunk':        # ResidualBlocksWithInputConv body: bufs [s0, s1, t, out]
+        bufs = [x, torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)]
+        layers, ci = [], 0
+        for i in range(nblk):
+            ni = 3 if i == nblk - 1 else 1 - ci
+            layers.append((2 * i, ci, -1, 2, ACT_RELU, ACT_NONE))
+            layers.append((2 * i + 1, 2, ci, ni, ACT_NONE, ACT_NONE))
+            ci = ni
+        out_idx = 3
+    else:                      # ResList: bufs [x, s0, s1, t, out]
+        bufs = [x] + [torch.empty_like(x) for _ in range(4)]
+        layers, cur = [], 0
+        for i in range(nblk):
+            nxt = 1 + (i % 2)
+            layers.append((2 * i, cur, -1, 3, ACT_LRELU02, ACT_NONE))
+            layers.append((2 * i + 1, 3, cur, nxt, ACT_NONE, ACT_LRELU02 if i == 1 else ACT_NONE))   # one act_post for coverage
+            cur = nxt
+        layers.append((2 * nblk, cur, 0, 4, ACT_NONE, ACT_NONE))
+        out_idx = 4
+    return bufs, layers, chain_l, conv_l, out_idx
+
+
+def _run_per_layer(cuda_ops, bufs, layers, conv_l):
+    for li, src, res, dst, a0, a1 in layers:
+        cuda_ops.conv2d(conv_l[li], bufs[src], None, bufs[dst], res=bufs[res] if res >= 0 else None, act_pre=a0, act_post=a1)
+
+
+@pytest.mark.parametrize('C,H,W,kind,nblk', [(48, 16, 8, 'trunk', 2), (48, 37, 53, 'trunk', 3), (48, 64, 96, 'reslist', 4),
+                                             (24, 40, 56, 'trunk', 3), (32, 33, 47, 'reslist', 2), (48, 135, 240, 'reslist', 4),
+                                             (48, 270, 480, 'trunk', 30), (48, 540, 960, 'reslist', 4)],
+                         ids=['1tile', 'odd', 'reslist', 'c24', 'c32', 'half', 'full_trunk', '2x_reslist'])
+@pytest.mark.parametrize('prec', ['bf16', 'fp16'])
+def test_conv_chain_matches_per_layer(cuda_ops, C, H, W, kind, nblk, prec):
+    dt = DT[prec]
+    bufs, layers, chain_l, conv_l, out_idx = _chain_case(cuda_ops, C, H, W, dt, kind, nblk)
+    x0 = bufs[0].clone()
+    _run_per_layer(cuda_ops, bufs, layers, conv_l)
+    torch.cuda.synchronize()
+    expect = bufs[out_idx].clone()
+    assert torch.isfinite(expect.float()).all() and expect.float().abs().max() > 1e-3
+    flags = torch.empty((((H + 15) // 16) * ((W + 7) // 8),), dtype=torch.int32, device='cuda')
+    for rep in range(4 if H * W <= 270 * 480 else 2):             # repeated: a dependency race would not be deterministic
+        for b in bufs[1:]:
+            b.fill_(float('nan'))
+        bufs[0].copy_(x0)
+        cuda_ops.conv_chain(bufs, [(chain_l[li], src, res, dst, a0, a1) for li, src, res, dst, a0, a1 in layers], flags)
+        torch.cuda.synchronize()
+        assert torch.equal(bufs[out_idx], expect), \
+            f'rep {rep}: {(bufs[out_idx].float() - expect.float()).abs().max().item():.3e} max abs, ' \
+            f'{(bufs[out_idx] != expect).float().mean().item():.3e} of the elements differ'
+        assert int(flags.min()) == len(layers) and int(flags.max()) == len(layers)
+
+
+def test_conv_chain_more_than_64_layers_and_errors(cuda_ops):
+    dt = torch.bfloat16
+    bufs, layers, chain_l, conv_l, out_idx = _chain_case(cuda_ops, 48, 48, 64, dt, 'trunk', 40)      # 80 layers -> two launches
+    x0 = bufs[0].clone()
+    _run_per_layer(cuda_ops, bufs, layers, conv_l)
+    expect = bufs[out_idx].clone()
+    bufs[0].copy_(x0)
+    flags = torch.empty((3 * 8,), dtype=torch.int32, device='cuda')
+    cuda_ops.conv_chain(bufs, [(chain_l[li], src, res, dst, a0, a1) for li, src, res, dst, a0, a1 in layers], flags)
+    assert torch.equal(bufs[out_idx], expect)
+    with pytest.raises(ValueError, match='own source'):
+        cuda_ops.conv_chain(bufs, [(chain_l[0], 0, -1, 0, 0, 0)], flags)

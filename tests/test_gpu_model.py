@@ -32,8 +32,43 @@ def test_fp32_path_matches_reference_golden(name):
         print(f'{name} window {k}: psnr {p:.1f} dB, max abs {err:.2e}')
         assert p >= 80.0, f'{name} window {k}: PSNR vs reference {p:.1f} dB'
         assert err <= 5e-3
-    # first window: matching products against the reference's own (hooked) outputs
-    st = net.Network._state[0]
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_first_window_products_match_reference_golden(name):
+    """flows / confidence / index maps of the FIRST window against the reference's own hooked outputs (make_golden.py:
+    flows_0 = fw j = 0..T-2 then bw for j = T-1..1; conf_0 / idx_0 per window frame) - fp32 path, so an index may only
+    differ on an exact score tie."""
+    from refvsr_b200.synth import sliding_windows
+    spec, cfg, net, lrs, refs, golden = build_case(name, 'cuda', b200_precision='fp32')
+    T, h, w = spec['T'], spec['h'], spec['w']
+    k, wl, wr, first = next(iter(sliding_windows(lrs, refs, T)))
+    net(wl.cuda(), wr.cuda(), True, False, False)
+    N = net.Network
+    mid = T // 2
+    gradio = False
+    if not gradio:
+        for j in range(0, mid + 1):                      # consumed forward flows (RefVSR.py:182-184)
+            if mid == T - 1 and j == mid:
+                continue
+            f = N._ring('fw', j, T, (h, w, 2)).cpu()
+            g = torch.from_numpy(golden['flows_0'][j]).permute(1, 2, 0)
+            assert (f - g).abs().max() <= 2e-3, f'forward flow {j}: {(f - g).abs().max():.2e} px'
+        for j in range(mid, T - 1):                      # backward flows: hook order j = T-1..1 -> index j-1 (RefVSR.py:187-189)
+            f = N._ring('bw', j, T, (h, w, 2)).cpu()
+            g = torch.from_numpy(golden['flows_0'][T - 1 + (T - 2 - j)]).permute(1, 2, 0)
+            assert (f - g).abs().max() <= 2e-3, f'backward flow {j}: {(f - g).abs().max():.2e} px'
+    flips = []
+    for i in range(T):
+        slot = N._frame_slot(i % T, h, w)
+        gi, gc = golden['idx_0'][i], golden['conf_0'][i, 0]
+        idx = slot['idx'].cpu().numpy()
+        conf = slot['conf'].cpu().numpy()
+        same = idx == gi.reshape(-1)
+        flips.append(1.0 - same.mean())
+        assert np.abs(conf - gc).max() <= 2e-3, f'frame {i}: conf {np.abs(conf - gc).max():.2e}'
+    print(f'{name}: index flip rate vs reference {np.mean(flips):.4%}')
+    assert np.mean(flips) <= 2e-3
 
 
 @pytest.mark.parametrize('name', list(CASES))
