@@ -148,6 +148,9 @@ typedef struct {
   const rv_chain_layer* layers; /* HOST array */
   int32_t nlayers;
   int32_t* flags;
+  int32_t max_ctas; /* 0: one persistent CTA per SM.  > 0: cap (leave SMs free for kernels of OTHER streams that must stay
+                       co-resident, e.g. NCCL point-to-point kernels: the chain's CTAs spin on each other's flags and all
+                       of them have to be resident) */
 } rv_conv_chain_desc;
 int rv_conv_chain(const rv_conv_chain_desc* d, void* stream);
 

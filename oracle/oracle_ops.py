@@ -191,7 +191,7 @@ class OracleOps:
                                      bias=bias.detach().float().cpu(), srcs=[(c, alloc)], stride=1, pad=1, cout=c,
                                      alloc0=alloc, alloc1=0)
 
-    def conv_chain(self, bufs, layers, flags):
+    def conv_chain(self, bufs, layers, flags, max_ctas=0):
         """the chain's contract: exactly the layers, one after the other"""
         for pk, src, res, dst, a0, a1 in layers:
             assert dst != src

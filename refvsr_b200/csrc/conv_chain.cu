@@ -177,13 +177,19 @@ conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ C
           __syncwarp();
         }
         const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-        if (l > 0) {
-          // tile-level dependency: the 3 x 3 tile neighbourhood (incl. the tile itself) has completed l layers
-          const int dy = lane / 3 - 1, dx = lane - (lane / 3) * 3 - 1;
+        if (l > 0 && (k % 3) == 0) {
+          // tile-level dependency: the 3 x 3 tile neighbourhood (incl. the tile itself) has completed l layers.  Checked for
+          // THREE local tiles per L2 round trip (lanes 0-8 / 9-17 / 18-26): one acquire round trip per tile (~0.7 us) would
+          // make this warp the pacing stage.  The extra tiles' dependencies are layer-(l-1) tiles of other CTAs, which never
+          // wait for a layer-l tile, so batching cannot deadlock.
+          const int j = lane / 9, nbr = lane - j * 9;
+          const int dy = nbr / 3 - 1, dx = nbr - (nbr / 3) * 3 - 1;
+          const int tj = tile + j * G;
+          const int tyj = tj / p.tiles_x, txj = tj - tyj * p.tiles_x;
           const int tiles_y = p.ntiles / p.tiles_x;
-          const int ny = ty + dy, nx = tx + dx;
-          const bool need = lane < 9 && ny >= 0 && ny < tiles_y && nx >= 0 && nx < p.tiles_x;
-          const int* f = p.flags + (need ? ny * p.tiles_x + nx : tile);
+          const int ny = tyj + dy, nx = txj + dx;
+          const bool need = lane < 27 && (k + j) < ntl && ny >= 0 && ny < tiles_y && nx >= 0 && nx < p.tiles_x;
+          const int* f = p.flags + (need ? ny * p.tiles_x + nx : 0);
           uint32_t spins = 0;
           while (true) {
             const int v = need ? ld_acquire(f) : l;
@@ -458,7 +464,8 @@ extern "C" int rv_conv_chain(const rv_conv_chain_desc* d, void* stream) {
   const size_t fixed = 1024 + 2048 + (size_t)p.w_bytes + (size_t)CH_NGRP * CH_STG_BYTES;
   RV_REQUIRE((size_t)max_smem > fixed + 2 * (size_t)CH_A_BYTES, "rv_conv_chain: shared memory too small");
   p.slots = (int)std::min<size_t>(CH_MAXSLOTS, ((size_t)max_smem - fixed) / CH_A_BYTES);
-  const int grid = std::min(num_sms, p.ntiles);
+  int grid = std::min(num_sms, p.ntiles);
+  if (d->max_ctas > 0) grid = std::min(grid, (int)d->max_ctas);
   p.nmma = std::max(1, std::min(std::min(CH_NMMA, p.ntiles / grid), p.slots));
   { const char* e = getenv("REFVSR_CHAIN_NMMA"); if (e && atoi(e) > 0) p.nmma = std::min(p.nmma, atoi(e)); }
   int last_write[CH_MAXB];

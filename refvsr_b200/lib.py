@@ -52,7 +52,7 @@ class rv_chain_layer(C.Structure):
 class rv_conv_chain_desc(C.Structure):
     _fields_ = [('buf', C.c_void_p * 6), ('nbuf', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C', C.c_int32),
                 ('dtype', C.c_int32), ('nb', C.c_int32), ('layers', C.POINTER(rv_chain_layer)), ('nlayers', C.c_int32),
-                ('flags', C.c_void_p)]
+                ('flags', C.c_void_p), ('max_ctas', C.c_int32)]
 
 
 CHAIN_MAX_LAYERS, CHAIN_MAX_BUFFERS = 64, 6
@@ -190,7 +190,7 @@ class CudaOps:
         d.out, d.out_cs = out.data_ptr(), out.shape[2]
         _check(self.lib, self.lib.rv_resblock(C.byref(d), self._stream()), f'rv_resblock[{rb.name}]')
 
-    def conv_chain(self, bufs, layers, flags):
+    def conv_chain(self, bufs, layers, flags, max_ctas=0):
         """bufs: list of (H, W, C) tensors of one dtype / geometry; layers: [(packing.PackedChainLayer, src, res, dst, act_pre,
         act_post)] with buffer indices (res = -1: none); flags: int32 scratch with >= ceil(H/16)*ceil(W/8) entries.
         Launches ceil(len(layers) / 64) persistent kernels (rv_conv_chain)."""
@@ -210,7 +210,7 @@ class CudaOps:
             for b, t in enumerate(bufs):
                 d.buf[b] = t.data_ptr()
             d.nbuf, d.H, d.W, d.C, d.dtype, d.nb = len(bufs), H, W, Cc, DTYPE_CODE[bufs[0].dtype], nb
-            d.layers, d.nlayers, d.flags = arr, len(part), flags.data_ptr()
+            d.layers, d.nlayers, d.flags, d.max_ctas = arr, len(part), flags.data_ptr(), int(max_ctas)
             _check(self.lib, self.lib.rv_conv_chain(C.byref(d), self._stream()), 'rv_conv_chain')
 
     def space_to_depth2(self, src, out):

@@ -91,6 +91,9 @@ class Network(nn.Module):
         # cross-layer persistent chain kernel (rv_conv_chain): the 60-conv propagation trunks and the ResList decoders as ONE
         # launch each, bit-identical to the per-layer path (csrc/conv_chain.cu)
         self.use_chain = bool(_cget(config, 'b200_conv_chain', True)) and not os.environ.get('REFVSR_NO_CHAIN')   # (env: A/B runs)
+        self.chain_max_ctas = int(_cget(config, 'b200_chain_max_ctas', 0))   # see rv_conv_chain_desc.max_ctas (dist.py sets it)
+        self._ring_mod = None
+        self._shard = None
         self._bufs = {}
         self._device = torch.device('cpu')
         self._b = 0
@@ -212,7 +215,7 @@ class Network(nn.Module):
     def _run_chain(self, bufs, layers):
         H, W = bufs[0].shape[0], bufs[0].shape[1]
         flags = self._buf('chain.flags', (((H + 15) // 16) * ((W + 7) // 8),), torch.int32)
-        self.ops.conv_chain(bufs, layers, flags)
+        self.ops.conv_chain(bufs, layers, flags, max_ctas=self.chain_max_ctas)
 
     def _reslist(self, prefix, n, x, out, tag):
         """ResList (RefVSR_/common.py:64-82): n x [x + conv2(lrelu0.2(conv1(x)))], conv_tail, + input."""
@@ -546,17 +549,21 @@ class Network(nn.Module):
                 work.append(('frame', a0 + j))
         return work
 
+    def _rm(self, t):
+        """ring length: T per-frame slots for the windowed forward, (owned frames + T - 1) for a frame-sharded clip"""
+        return self._ring_mod or t
+
     def _ring(self, kind, a, t, shape, dtype=torch.float32):
-        return self._buf(f'ring{self._b}.{kind}.{a % t}', shape, dtype)
+        return self._buf(f'ring{self._b}.{kind}.{a % self._rm(t)}', shape, dtype)
 
     def _run_products(self, work, t, h, w, hr, wr):
         for kind, a in work:
             lr = self._ring('lr32', a, t, (3, h, w))
             if kind == 'pyr':
-                self._pyramid(lr, a % t)
+                self._pyramid(lr, a % self._rm(t))
             elif kind in ('fw', 'bw'):
-                pa = [self._buf(f'ring{self._b}.pyr{l}.{a % t}', (H, W, 3), torch.float32) for l, (H, W) in enumerate(self._pyr_shapes(h, w))]
-                pb = [self._buf(f'ring{self._b}.pyr{l}.{(a + 1) % t}', (H, W, 3), torch.float32) for l, (H, W) in enumerate(self._pyr_shapes(h, w))]
+                pa = [self._buf(f'ring{self._b}.pyr{l}.{a % self._rm(t)}', (H, W, 3), torch.float32) for l, (H, W) in enumerate(self._pyr_shapes(h, w))]
+                pb = [self._buf(f'ring{self._b}.pyr{l}.{(a + 1) % self._rm(t)}', (H, W, 3), torch.float32) for l, (H, W) in enumerate(self._pyr_shapes(h, w))]
                 out = self._ring(kind, a, t, (h, w, 2))
                 if kind == 'fw':
                     self._spynet(pb, pa, out)      # Flow(frame a+1, frame a)
@@ -565,7 +572,7 @@ class Network(nn.Module):
             elif kind in ('fw0', 'bw0'):
                 self._ring(kind[:2], a, t, (h, w, 2)).zero_()
             else:
-                self._frame_alignment(lr, self._ring('ref32', a, t, (3, hr, wr)), a % t)
+                self._frame_alignment(lr, self._ring('ref32', a, t, (3, hr, wr)), a % self._rm(t))
 
     # ------------------------------------------------------------------------------------------
     # forward (RefVSR.py:151-325)
@@ -717,21 +724,12 @@ class Network(nn.Module):
             return False
         return True
 
-    def _run_window(self, b, st, a0, t, h, w, hr, wr, work, is_first_frame, range_start, is_log, is_train):
-        """All kernel launches of one window.  Reads / writes static buffers only (graph-capturable)."""
+    def _backward_branch(self, a0, t, h, w, vis=None):
+        """backward branch of the window at stream position a0 (RefVSR.py:211-238): window-local, starts from zeros at the
+        window's last frame -> (feat_prop_UP, conf_map_prop) buffers at the centre frame"""
         ops = self.ops
         C, dt = self.mid_channels, self.act_dtype
         mid = t // 2
-        self._run_products(work, t, h, w, hr, wr)
-        vis = {'vis': collections.OrderedDict()} if is_log else None
-
-        def frame(i):
-            return self._frame_slot((a0 + i) % t, h, w)
-
-        def lr32(i):
-            return self._ring('lr32', a0 + i, t, (3, h, w))
-
-        # ---------------- backward branch (RefVSR.py:211-238) ----------------
         feat_prop = self._buf('bw.z.feat', (h, w, C), dt).zero_()
         feat_prop_UP = self._buf('bw.z.featUP', (2 * h, 2 * w, C), dt).zero_()
         conf_prop = self._buf('bw.z.conf', (h, w), torch.float32).zero_()
@@ -745,51 +743,70 @@ class Network(nn.Module):
                 wu = self._buf('bw.w.featUP', (2 * h, 2 * w, C), dt)
                 ops.warp(feat_prop_UP, flow, wu, flow_up2=True)                # RefVSR.py:220
                 feat_prop, conf_prop, feat_prop_UP = wf, wc, wu
-                if is_log and i == mid:
-                    vis['vis']['BW_LR_next_warp'] = self._warp_image(lr32(i + 1), flow)
-            fp = frame(i)
+                if vis is not None and i == mid:
+                    vis['vis']['BW_LR_next_warp'] = self._warp_image(self._ring('lr32', a0 + i + 1, t, (3, h, w)), flow)
+            fp = self._frame_slot((a0 + i) % self._rm(t), h, w)
             agg = self._prop_resblocks('backward_resblocks', fp['lr8'], feat_prop,
                                        self._buf('bw.agg', (h, w, C), dt), 'bw.rb')
             feat_prop, feat_prop_UP, conf_prop = self._rap(fp, conf_prop, agg, feat_prop_UP, f'bw.rap{i % 2}')
-        backward_feat_UP, conf_bw = feat_prop_UP, conf_prop
+        return feat_prop_UP, conf_prop
+
+    def _forward_step(self, a, t, h, w, state, flow, quirk, tagi):
+        """One forward-branch step at stream position `a` (RefVSR.py:248-277).  `state` = (feat, featUP, conf) or None (start
+        from zeros, no warp).  quirk=True: the step follows another step of the SAME call - the reference then warps the
+        already-warped LR-resolution feat_prop onto the 2x grid and drops the propagated feat_prop_UP (RefVSR.py:252-254);
+        quirk=False: the state comes from the previous call and feat_prop_UP is warped itself (RefVSR.py:256-260)."""
+        ops = self.ops
+        C, dt = self.mid_channels, self.act_dtype
+        if state is None:
+            feat_prop = self._buf('fw.z.feat', (h, w, C), dt).zero_()
+            feat_prop_UP = self._buf('fw.z.featUP', (2 * h, 2 * w, C), dt).zero_()
+            conf_prop = self._buf('fw.z.conf', (h, w), torch.float32).zero_()
+        else:
+            feat, featUP, conf = state
+            wf = self._buf('fw.w.feat', (h, w, C), dt)
+            ops.warp(feat, flow, wf)
+            wu = self._buf('fw.w.featUP', (2 * h, 2 * w, C), dt)
+            ops.warp(wf if quirk else featUP, flow, wu, flow_up2=True)
+            wc = self._buf('fw.w.conf', (h, w), torch.float32)
+            ops.warp(conf, flow, wc)
+            feat_prop, feat_prop_UP, conf_prop = wf, wu, wc
+        fp = self._frame_slot(a % self._rm(t), h, w)
+        agg = self._prop_resblocks('forward_resblocks', fp['lr8'], feat_prop, self._buf('fw.agg', (h, w, C), dt), 'fw.rb')
+        return self._rap(fp, conf_prop, agg, feat_prop_UP, f'fw.rap{tagi % 2}')
+
+    def _run_window(self, b, st, a0, t, h, w, hr, wr, work, is_first_frame, range_start, is_log, is_train):
+        """All kernel launches of one window.  Reads / writes static buffers only (graph-capturable)."""
+        C, dt = self.mid_channels, self.act_dtype
+        mid = t // 2
+        self._run_products(work, t, h, w, hr, wr)
+        vis = {'vis': collections.OrderedDict()} if is_log else None
+
+        def lr32(i):
+            return self._ring('lr32', a0 + i, t, (3, h, w))
+
+        # ---------------- backward branch (RefVSR.py:211-238) ----------------
+        backward_feat_UP, conf_bw = self._backward_branch(a0, t, h, w, vis)
         # (the forward branch writes 'fw.*' buffers only, so these stay intact)
 
         # ---------------- forward branch (RefVSR.py:241-283) ----------------
         if is_first_frame:
-            feat_prop = self._buf('fw.z.feat', (h, w, C), dt).zero_()
-            feat_prop_UP = self._buf('fw.z.featUP', (2 * h, 2 * w, C), dt).zero_()
-            conf_prop = self._buf('fw.z.conf', (h, w), torch.float32).zero_()
             range_start = 0
         prev = {'feat': self._buf(f'prev{b}.feat', (h, w, C), dt), 'featUP': self._buf(f'prev{b}.featUP', (2 * h, 2 * w, C), dt),
                 'conf': self._buf(f'prev{b}.conf', (h, w), torch.float32), 'flow': self._buf(f'prev{b}.flow', (h, w, 2), torch.float32)}
-        flow = None
+        state, flow = None, None
         for i in range(range_start, mid + 1):
             if i > range_start:
                 flow = self._ring('fw', a0 + i - 1, t, (h, w, 2))
-                wf = self._buf('fw.w.feat', (h, w, C), dt)
-                ops.warp(feat_prop, flow, wf)
-                # quirk kept on purpose: the LR-resolution feat_prop (already warped once) is warped onto
-                # the 2x grid, the propagated feat_prop_UP is dropped (RefVSR.py:252-254)
-                wu = self._buf('fw.w.featUP', (2 * h, 2 * w, C), dt)
-                ops.warp(wf, flow, wu, flow_up2=True)
-                wc = self._buf('fw.w.conf', (h, w), torch.float32)
-                ops.warp(conf_prop, flow, wc)
-                feat_prop, feat_prop_UP, conf_prop = wf, wu, wc
-            elif i == range_start and not is_first_frame:
+                state = self._forward_step(a0 + i, t, h, w, state, flow, True, i)
+            elif not is_first_frame:
                 flow = prev['flow']
-                wf = self._buf('fw.w.feat', (h, w, C), dt)
-                ops.warp(prev['feat'], flow, wf)
-                wu = self._buf('fw.w.featUP', (2 * h, 2 * w, C), dt)
-                ops.warp(prev['featUP'], flow, wu, flow_up2=True)              # RefVSR.py:259
-                wc = self._buf('fw.w.conf', (h, w), torch.float32)
-                ops.warp(prev['conf'], flow, wc)
-                feat_prop, feat_prop_UP, conf_prop = wf, wu, wc
+                state = self._forward_step(a0 + i, t, h, w, (prev['feat'], prev['featUP'], prev['conf']), flow, False, i)
+            else:
+                state = self._forward_step(a0 + i, t, h, w, None, None, False, i)
             if is_log and i == mid and flow is not None:
                 vis['vis']['FW_LR_prev_warp'] = self._warp_image(lr32(i - 1), flow)
-            fp = frame(i)
-            agg = self._prop_resblocks('forward_resblocks', fp['lr8'], feat_prop,
-                                       self._buf('fw.agg', (h, w, C), dt), 'fw.rb')
-            feat_prop, feat_prop_UP, conf_prop = self._rap(fp, conf_prop, agg, feat_prop_UP, f'fw.rap{i % 2}')
+            feat_prop, feat_prop_UP, conf_prop = state
             if (is_train and i == 0) or (not is_train and i == mid):           # RefVSR.py:279-283
                 prev['feat'].copy_(feat_prop)
                 prev['featUP'].copy_(feat_prop_UP)
@@ -802,12 +819,147 @@ class Network(nn.Module):
 
         if is_log and _cget(self.config, 'save_sample', False):
             ev = collections.OrderedDict()
-            ev['conf_map'] = frame(mid)['conf'].view(1, 1, h, w).clone()
+            ev['conf_map'] = self._frame_slot((a0 + mid) % self._rm(t), h, w)['conf'].view(1, 1, h, w).clone()
             ev['conf_map_prop_backward'] = conf_bw.view(1, 1, h, w).clone()
             ev['conf_map_prop_forward'] = conf_prop.view(1, 1, h, w).clone()
             ev['conf_map_prop'] = torch.maximum(ev['conf_map_prop_backward'], ev['conf_map_prop_forward'])
             vis['eval_vis'] = ev
         return out, vis
+
+    # ------------------------------------------------------------------------------------------
+    # frame-sharded clip (refvsr_b200/dist.py): the same steps, scheduled per ROLE instead of per window.
+    # A rank owns output frames [f0, f1).  Stream position a holds clip frame clamp(a - T//2, 0, n-1) (the clamped windows of
+    # data_loader/datasets.py:233-234); window k covers positions k .. k+T-1.  Per-frame products live in a ring of
+    # (f1 - f0) + T - 1 positions.  Forward-branch steps form a serial chain across ranks (state hand-off); backward
+    # branches, products and the upsampling tail are local.
+    # ------------------------------------------------------------------------------------------
+    def shard_begin(self, frames_lr, frames_ref, g0, own, num_frames):
+        """frames_*: clip frames [g0, g0 + m) (own range + input halo), (m, 3, h, w) on the compute device."""
+        t = self.config.frame_num
+        m, _, h, w = frames_lr.shape
+        hr, wr = frames_ref.shape[2], frames_ref.shape[3]
+        if self.max_frame_itr_num is None:
+            raise ValueError('reset_branch=None: the forward recurrence never restarts; frame sharding needs chain heads only at '
+                             'frame 0, i.e. a pure pipeline - run replicas over different clips instead')
+        self._device = frames_lr.device
+        self._b = 0
+        self._ring_mod = (own[1] - own[0]) + t - 1
+        self._shard = {'pyr': set(), 'fw': set(), 'bw': set(), 'frame': set(), 'staged': set(), 'geom': (t, h, w, hr, wr),
+                       'g0': g0, 'n': num_frames, 'own': tuple(own), 'lr': frames_lr, 'ref': frames_ref, 'fw_out': {}}
+        self._state.clear()          # the windowed forward's caches are void once the ring is re-purposed
+
+    def shard_end(self):
+        self._ring_mod, self._shard = None, None
+        self._state.clear()
+
+    def _shard_products(self, want):
+        """make sure the per-position products in `want` = [(kind, a)], kind in frame / fw / bw, exist in the ring"""
+        st = self._shard
+        t, h, w, hr, wr = st['geom']
+        mid, n, g0 = t // 2, st['n'], st['g0']
+        ev = _cget(self.config, 'EVAL', None)
+        zero_flow = bool(_cget(ev, 'is_gradio', False)) if ev is not None else False
+        work = []
+
+        def stage(a):
+            if a not in st['staged']:
+                c = min(max(a - mid, 0), n - 1) - g0
+                if not 0 <= c < st['lr'].shape[0]:
+                    raise RuntimeError(f'frame-sharded clip: position {a} needs clip frame {c + g0}, outside the local range '
+                                       f'[{g0}, {g0 + st["lr"].shape[0]}) - input halo too small')
+                self._ring('lr32', a, t, (3, h, w)).copy_(st['lr'][c])
+                self._ring('ref32', a, t, (3, hr, wr)).copy_(st['ref'][c])
+                st['staged'].add(a)
+
+        def need_pyr(a):
+            stage(a)
+            if a not in st['pyr']:
+                st['pyr'].add(a)
+                work.append(('pyr', a))
+        for kind, a in want:
+            if a in st[kind]:
+                continue
+            st[kind].add(a)
+            if kind == 'frame':
+                stage(a)
+                work.append(('frame', a))
+            elif zero_flow:
+                work.append((kind + '0', a))
+            else:
+                need_pyr(a)
+                need_pyr(a + 1)
+                work.append((kind, a))
+        n0 = self.ops.launch_count()
+        self._run_products(work, t, h, w, hr, wr)
+        self.executed_kernels += self.ops.launch_count() - n0
+
+    def shard_state_buffers(self, tag):
+        """persistent (feat, featUP, conf) buffers for a propagated forward state (`tag`: 'in' = received, 'out' = to send)"""
+        t, h, w, hr, wr = self._shard['geom']
+        C, dt = self.mid_channels, self.act_dtype
+        return (self._buf(f'sh.{tag}.feat', (h, w, C), dt), self._buf(f'sh.{tag}.featUP', (2 * h, 2 * w, C), dt),
+                self._buf(f'sh.{tag}.conf', (h, w), torch.float32))
+
+    def shard_prefetch_forward(self, k0, k1, head):
+        """everything the forward steps of output frames [k0, k1) need that does NOT depend on the incoming state"""
+        t = self._shard['geom'][0]
+        mid, n = t // 2, self._shard['n']
+        want = []
+        for k in range(k0, k1):
+            first = head and k == k0
+            for i in range(0 if first else mid, mid + 1):
+                want.append(('frame', k + i))
+            for j in range(0 if first else mid - 1, mid):
+                want.append(('fw', k + j))            # fw(a) = Flow(position a+1, position a); the step at k+i warps with fw(k+i-1)
+        self._shard_products(want)
+
+    def shard_forward_piece(self, k0, k1, state_in):
+        """Forward-branch steps of output frames [k0, k1) with torch.no_grad().  state_in None: k0 is a chain head
+        (k0 % reset_branch == 0: the branch restarts from zeros over the window's first T//2+1 frames, RefVSR.py:168-176);
+        else (feat, featUP, conf) after frame k0-1.  Returns the state after frame k1-1 (persistent 'out' buffers)."""
+        st = self._shard
+        t, h, w, hr, wr = st['geom']
+        mid = t // 2
+        with torch.no_grad():
+            self.shard_prefetch_forward(k0, k1, state_in is None)
+            n0 = self.ops.launch_count()
+            out_state = self.shard_state_buffers('out')
+            state = state_in
+            for k in range(k0, k1):
+                if k == k0 and state_in is None:
+                    state = None
+                    for i in range(0, mid + 1):
+                        flow = self._ring('fw', k + i - 1, t, (h, w, 2)) if i > 0 else None
+                        state = self._forward_step(k + i, t, h, w, state, flow, True, i)
+                else:
+                    flow = self._ring('fw', k + mid - 1, t, (h, w, 2))       # = forward_flow_prev of the previous call
+                    state = self._forward_step(k + mid, t, h, w, state, flow, False, mid)
+                for dst, src in zip(out_state, state):                      # RefVSR.py:279-283 (detach().clone())
+                    dst.copy_(src)
+                state = out_state
+                C, dt = self.mid_channels, self.act_dtype
+                keep = (self._buf(f'sh.fwUP.{k - st["own"][0]}', (2 * h, 2 * w, C), dt),
+                        self._buf(f'sh.fwconf.{k - st["own"][0]}', (h, w), torch.float32))
+                keep[0].copy_(out_state[1])
+                keep[1].copy_(out_state[2])
+                st['fw_out'][k] = keep
+            self.executed_kernels += self.ops.launch_count() - n0
+        return out_state
+
+    def shard_finish_window(self, k):
+        """backward branch (window-local) + upsampling tail of output frame k; its forward step must be done.
+        -> (3, 4h, 4w) fp32 (a fresh tensor)"""
+        st = self._shard
+        t, h, w, hr, wr = st['geom']
+        mid = t // 2
+        with torch.no_grad():
+            self._shard_products([('frame', k + i) for i in range(mid, t)] + [('bw', k + j) for j in range(mid, t - 1)])
+            n0 = self.ops.launch_count()
+            bw_up, conf_bw = self._backward_branch(k, t, h, w)
+            fw_up, conf_fw = st['fw_out'][k]
+            out = self._compute_up(bw_up, fw_up, conf_bw, conf_fw, self._ring('lr32', k + mid, t, (3, h, w)), clamp01=True)
+            self.executed_kernels += self.ops.launch_count() - n0
+            return out.clone()
 
     def _warp_image(self, img, flow):
         """debug visualisation `warp(lrs[:, i±1], flow)` (RefVSR.py:222,263) -> (1,3,h,w)"""

@@ -240,7 +240,7 @@ def test_conv_chain_schedule_is_the_per_layer_schedule(oracle_ops, monkeypatch):
         calls = {'n': 0, 'layers': 0}
         orig = oracle_ops.conv_chain
 
-        def counting(bufs, layers, flags, _o=orig, _c=calls):
+        def counting(bufs, layers, flags, max_ctas=0, _o=orig, _c=calls):
             _c['n'] += 1
             _c['layers'] += len(layers)
             return _o(bufs, layers, flags)
