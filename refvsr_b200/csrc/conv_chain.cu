@@ -493,17 +493,16 @@ extern "C" int rv_conv_chain(const rv_conv_chain_desc* d, void* stream) {
   const size_t smem = 1024 + (size_t)p.slots * CH_A_BYTES + p.w_bytes + (size_t)CH_NGRP * CH_STG_BYTES;
   cudaStream_t st = (cudaStream_t)stream;
   RV_CUDA_OK(cudaMemsetAsync(d->flags, 0, (size_t)p.ntiles * sizeof(int), st));
-  auto launch = [&](auto kern) -> int {
-    static size_t configured = 0;
-    if (smem > configured) {
-      RV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
-    kern<<<grid, 32 * (1 + CH_NMMA) + 128 * CH_NGRP, smem, st>>>(maps, p);
-    return RV_OK;
-  };
-  int rc = (d->dtype == RV_BF16) ? launch(conv_chain_kernel<__nv_bfloat16>) : launch(conv_chain_kernel<__half>);
-  if (rc) return rc;
+  // (one "configured" high-water mark per instantiation: both kernels have the same function-pointer TYPE, so a static inside
+  //  a generic lambda would be shared and the second dtype would launch without its shared-memory attribute)
+  static size_t configured[2] = {0, 0};
+  const int ki = d->dtype == RV_BF16 ? 1 : 0;
+  void (*kern)(ChMaps, ChP) = ki ? conv_chain_kernel<__nv_bfloat16> : conv_chain_kernel<__half>;
+  if (smem > configured[ki]) {
+    RV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[ki] = smem;
+  }
+  kern<<<grid, 32 * (1 + CH_NMMA) + 128 * CH_NGRP, smem, st>>>(maps, p);
   RV_LAUNCH_CHECK("conv_chain");
   return RV_OK;
 }

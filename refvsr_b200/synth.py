@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 
 
-def make_clip(num_frames, h, w, ref_scale=1, seed=1234):
+def make_clip(num_frames, h, w, ref_scale=1, seed=1234, return_hr=False):
     g = torch.Generator(device='cpu').manual_seed(seed)
     H, W = 4 * h, 4 * w
     mx, my = 6 * num_frames + 8, 3 * num_frames + 8          # margins for the translation (HR pixels)
@@ -17,15 +17,18 @@ def make_clip(num_frames, h, w, ref_scale=1, seed=1234):
         lo = torch.rand(1, 3, ch // s + 3, cw // s + 3, generator=g)
         scene = scene + amp * F.interpolate(lo, size=(ch, cw), mode='bicubic', align_corners=False)
     scene = (scene + 0.04 * torch.randn(1, 3, ch, cw, generator=g)).clamp(0, 1)
-    lrs, refs = [], []
+    lrs, refs, hrs = [], [], []
     for k in range(num_frames):
         ox, oy = mx + 6 * k, my - 3 * k
         oy = max(0, min(oy, ch - H))
         hr = scene[:, :, oy:oy + H, ox:ox + W]
         lrs.append(F.avg_pool2d(hr, 4))
+        hrs.append(hr)
         cy, cx = H // 4, W // 4                              # centre half-FoV crop (2h x 2w HR pixels... x2)
         crop = hr[:, :, cy:cy + H // 2, cx:cx + W // 2]      # (2h, 2w)
         refs.append(crop if ref_scale == 2 else F.avg_pool2d(crop, 2))
+    if return_hr:
+        return torch.cat(lrs, 0).contiguous(), torch.cat(refs, 0).contiguous(), torch.cat(hrs, 0).contiguous()
     return torch.cat(lrs, 0).contiguous(), torch.cat(refs, 0).contiguous()
 
 

@@ -35,8 +35,9 @@ def make_tree(root, h, w, videos=2, frames=3, seed=5):
     import cv2
     from refvsr_b200.synth import make_clip
     for v in range(videos):
-        lrs, refs = make_clip(frames, h, w, 1, seed=seed + v)
-        hr = torch.nn.functional.interpolate(lrs, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
+        # ground truth = the HR scene the LR frames were area-downsampled from (NOT bicubic(LR): with GT == the network's own
+        # bicubic base the printed PSNR would measure nothing but the residual branch and amplify any difference in it)
+        lrs, refs, hr = make_clip(frames, h, w, 1, seed=seed + v, return_hr=True)
         x2 = torch.nn.functional.interpolate(lrs, scale_factor=2, mode='bicubic', align_corners=False).clamp(0, 1)
         for res, uw, wide in (('LRx4', lrs, refs), ('LRx2', x2, x2), ('HR', hr, hr)):
             for cam, t in (('UW', uw), ('W', wide), ('T', wide)):
