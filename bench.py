@@ -197,7 +197,7 @@ def kernel_rooflines(net, peaks):
     out['warp_up'] = dict(bound='hbm', achieved=byt / twarp / 1e9, peak=peaks['hbm'], unit='GB/s',
                           frac=byt / twarp / 1e9 / peaks['hbm'], seconds=twarp, algorithmic_bytes=byt)
     # the same trunk as ONE persistent launch (rv_conv_chain): 30 residual blocks = 60 convs over L2-resident ping-pong maps
-    if getattr(net.Network, 'use_chain', False) and dt != torch.float32 and hasattr(ops, 'conv_chain') and C <= 48:
+    if dt != torch.float32 and hasattr(ops, 'conv_chain') and C <= 48:          # (opt-in kernel, reported as evidence)
         from refvsr_b200.lib import ACT_NONE
         nblk = 30
         cl = [packing.pack_chain(f'bench.ch{i}', w * (1.0 if i % 2 == 0 else 0.3), torch.zeros(C), C, dt, dev) for i in range(2 * nblk)]
@@ -212,7 +212,7 @@ def kernel_rooflines(net, peaks):
         tch = timeit(lambda i: ops.conv_chain(cb, layers, flags), iters=10, warm=2) / (2 * nblk)
         out['conv3x3_lr_chain'] = dict(bound='tensor', achieved=flops / tch / 1e12, peak=peaks['tensor_burst'], unit='TFLOP/s',
                                        frac=flops / tch / 1e12 / peaks['tensor_burst'], seconds=tch, algorithmic_flops=flops,
-                                       note='per layer of a 60-layer rv_conv_chain launch (activations stay in L2)')
+                                       note='per layer of a 60-layer rv_conv_chain launch (opt-in: slower than per-layer launches, profiles/r02_conv_chain.md)')
     # K3 / K4 / K7: the remaining HBM kernels of the north_star's >= 60 % list
     idx = torch.randint(0, (H // 2) * (W // 2), (H * W,), device=dev, dtype=torch.int32)
     vd = [torch.randn((H // 2, W // 2, C), device=dev).to(dt) for _ in range(nrot)]
@@ -377,6 +377,69 @@ def eager_b200(workload, dev, windows=3):
             torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
             torch.cuda.empty_cache()
     return out
+
+
+def clip_leg(args, net, dev, world, rank, wl):
+    """One clip of --clip-frames frames (default 32), every rank owning a contiguous range of OUTPUT frames (32 / 8 = 4 per
+    GPU), i.e. finer than the 9-frame reset segments.  Timed with CUDA events from before the input-halo exchange to after the
+    last owned frame, barrier on both sides, max over ranks; one untimed full pass first (allocations, NCCL connections).
+    Strong scaling: the same 32 frames at every N; at N = 1 it is the single-stream time of the same code path (eager
+    launches - the per-window CUDA graphs belong to the windowed API)."""
+    import torch
+    import torch.distributed as dist
+    from refvsr_b200.dist import exchange_halo, plan_frames, run_clip_frame_sharded
+    from refvsr_b200.synth import make_clip_range
+    n = args.clip_frames
+    plan = plan_frames(n, world)
+    f0, f1 = plan[rank]
+    groups = None
+    if world > 1:
+        groups = [dist.new_group(list(range(world))), dist.new_group(list(range(world)))]
+        # the chain kernels' CTAs spin on each other's flags and must all be resident next to the NCCL point-to-point kernels
+        # (a posted receive / an unmatched send stays resident): leave those SMs free
+        net.Network.chain_max_ctas = max(16, torch.cuda.get_device_properties(dev).multi_processor_count - 16)
+    own_l, own_r = make_clip_range(f0, f1 - f0, H, W, wl['ref_scale'], seed=4321)
+    own_l, own_r = own_l.to(dev), own_r.to(dev)
+    info = {}
+
+    def one_pass(timing=None):
+        if world > 1:
+            fl, first = exchange_halo(own_l, plan, rank, T // 2)
+            fr, _ = exchange_halo(own_r, plan, rank, T // 2)
+        else:
+            fl, fr, first = own_l, own_r, 0
+        return run_clip_frame_sharded(net, fl, fr, first, plan, rank, groups=groups, timing=timing)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    one_pass()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = net.Network.executed_kernels
+    e0.record()
+    res = one_pass(info)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    net.Network.chain_max_ctas = 0
+    chk = float(sum(r.double().mean() for _, r in res)) if res else 0.0
+    if world > 1:
+        c = torch.tensor([chk], device=dev, dtype=torch.float64)
+        dist.all_reduce(c)
+        chk = float(c.item())
+    return {'value': n / (ms * 1e-3), 'unit': 'frames/s', 'frames': n, 'ms_total': ms, 'scaling': 'strong', 'n_gpus': world,
+            'plan': [list(p) for p in plan], 'rank0_launches': int(net.Network.executed_kernels - n0),
+            'rank0_schedule': [list(map(str, e)) for e in info.get('log', [])][:24],
+            'mean_of_frame_means': chk / n,
+            'note': 'time to the last frame of ONE clip incl. the T//2-frame input-halo exchange and the forward-state hand-offs '
+                    '(62 MB per rank boundary inside a reset segment); the forward chain is serial inside each 9-frame segment '
+                    '(1 of 5 propagation steps per frame), backward branches / per-frame products / upsampling tails are local'}
 
 
 def run_ours(args):
@@ -568,6 +631,15 @@ def run_ours(args):
                      'ms_per_step': sus_ms / (n_sus - Wm), 'clocks': ck}
         del sl, sr
 
+    # BASELINE configs[3]: ONE 32-frame clip sharded by frames over all GPUs (strong scaling): time to the last frame,
+    # including the input-halo exchange and the forward-state hand-offs (refvsr_b200/dist.py::run_clip_frame_sharded)
+    clip = None
+    if not args.no_clip:
+        try:
+            clip = clip_leg(args, net, dev, world, rank, wl)
+        except Exception as ex:                                  # noqa: BLE001  (never take the main measurement down)
+            clip = {'error': repr(ex)[:300]}
+
     line = None
     if rank == 0:
         fps = world * K / ((ms_res + halo_ms) * 1e-3)
@@ -601,6 +673,8 @@ def run_ours(args):
         }
         if sustained is not None:
             line['sustained'] = sustained
+        if clip is not None:
+            line['clip32'] = clip
         if world == 1 and not args.no_eager:
             del lrs_d, refs_d
             net.Network._bufs.clear()
@@ -671,6 +745,8 @@ def main():
     ap.add_argument('--precision', default=None, choices=[None, 'fp32', 'fp16', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-eager', action='store_true', help='skip the eager-PyTorch-reference-on-this-GPU leg')
+    ap.add_argument('--no-clip', action='store_true', help='skip the 32-frame frame-sharded clip leg (BASELINE configs[3])')
+    ap.add_argument('--clip-frames', type=int, default=32)
     ap.add_argument('--no-sustained', action='store_true', help='skip the >= 5 s sustained leg')
     ap.add_argument('--sustained-s', type=float, default=5.0)
     ap.add_argument('--no-graphs', action='store_true', help='eager kernel launches (for ncu launch lists)')

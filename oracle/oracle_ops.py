@@ -133,6 +133,11 @@ class OracleOps:
         out.copy_(_nhwc(f))
 
     # ---- warp ----
+    def warp3(self, feat, featUP, conf, flow, out_feat, out_featUP, out_conf):
+        self.warp(feat, flow, out_feat)
+        self.warp(conf, flow, out_conf)
+        self.warp(featUP, flow, out_featUP, flow_up2=True)
+
     def warp(self, src, flow, out, flow_up2=False):
         x = _nchw(src if src.dim() == 3 else src.unsqueeze(-1))
         f = _nchw(flow)

@@ -22,6 +22,12 @@
 //     non-coherent path: the data was written by other SMs during this same launch).
 //   * weights of the next layer replace the current ones as soon as the last MMA of the layer has retired (mbarrier fed by
 //     tcgen05.commit of every issuing warp); up to slots-1 boxes of the next layer are prefetched before that.
+// MEASURED OUTCOME (round 2, B200; profiles/r02_conv_chain.md): bit-identical to the per-layer path at every size, but SLOWER -
+// 20-22 us per 270x480 layer against 9.8 us for one conv_tc launch, 55 vs 32 us at 540x960.  The device timeline shows why:
+// a cross-CTA dependency hop (epilogue -> store complete -> release -> poll -> acquire -> TMA load) costs ~15k cycles on this
+// two-die part (GPU-scope fences 2-4k cycles each), while a CTA has only 7 tiles = ~10k cycles of MMA work per layer to hide
+// it behind, and the neighbourhood of tile k reaches tile k+1 of the previous layer.  The ~3.6 us a launch boundary costs is
+// cheaper than per-tile GPU-scope synchronisation.  The kernel therefore ships OPT-IN (config.b200_conv_chain = True).
 // Geometry = conv_tc.cu MODE 1 (validated in round 1): tile 16 rows x 8 columns = 128 TMEM lanes, ONE 18 x 10 pixel box
 // per tile (64-channel rows, SWIZZLE_128B, out-of-bounds zero fill = conv padding), the 9 taps are row-shifted UMMA
 // descriptor views of it; 512 threads = TMA producer warp, 3 MMA-issuing warps, 3 epilogue groups of 4 warps.
@@ -55,6 +61,8 @@ struct ChP {
   int H, W, C, NB, tiles_x, ntiles, nlayers, slots, nmma, fmt, ksteps;
   uint32_t w_bytes;
   int* flags;
+  long long* trace;         // REFVSR_CHAIN_TRACE=<device ptr>: clock64 timeline of CTA `trace_cta` ([7 roles][2048][3])
+  int trace_cta;
   const void* buf[CH_MAXB];
   ChLayer layer[CH_MAXL];
 };
@@ -80,9 +88,11 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ int ld_acquire(const int* p) {
+// coherent at GPU scope, but WITHOUT the L1 invalidation an acquire load carries (CCTL.IVALL per poll iteration evicted the
+// epilogue's read-only data and cost an L2 round trip per tile - profiles/r02_conv_chain.md)
+__device__ __forceinline__ int ld_relaxed(const int* p) {
   int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ uint4 ld_cg16(const void* p) {
@@ -103,7 +113,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void publish(int* flag, int val) {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   asm volatile("fence.proxy.async;" ::: "memory");
-  __threadfence();
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(val) : "memory");
+}
+// same, when exactly one newer bulk store (just issued) may still be in flight
+__device__ __forceinline__ void publish_prev(int* flag, int val) {
+  asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+  asm volatile("fence.proxy.async;" ::: "memory");
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(val) : "memory");
 }
 
@@ -120,12 +135,22 @@ __device__ __forceinline__ float2 unpack2h(uint32_t v, __nv_bfloat16) {
   return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
 }
 
+// device timeline (tools/chain_trace.py): role r appends (event, n, clock64) triples; one uniform branch when disabled
+#define CH_TRACE(role, ev, nn)                                                                         \
+  do {                                                                                                 \
+    if (p.trace != nullptr && (int)blockIdx.x == p.trace_cta && (threadIdx.x & 31) == 0 && tr_n < 2048) { \
+      long long* _t = p.trace + ((size_t)(role) * 2048 + tr_n) * 3;                                   \
+      _t[0] = (ev); _t[1] = (long long)(nn); _t[2] = clock64(); ++tr_n;                                \
+    }                                                                                                  \
+  } while (0)
+
 template <typename T>
 __global__ void __launch_bounds__(32 * (1 + CH_NMMA) + 128 * CH_NGRP, 1)
 conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ ChP p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[CH_MAXSLOTS], bar_empty[CH_MAXSLOTS], bar_w, bar_wfree, bar_tfull[CH_NACC], bar_tempty[CH_NACC];
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float bias_s[4][64];     // bias of layer l in slot l & 3 (arrives with the weights, on bar_w)
 
   const uint32_t raw = tc::smem_u32(smem_raw);
   uint8_t* smemA = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -137,6 +162,8 @@ conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ C
   const int G = gridDim.x;
   const int ntl = (p.ntiles - (int)blockIdx.x + G - 1) / G;      // local tiles per layer: cta, cta + G, ...
   const uint32_t total = (uint32_t)p.nlayers * (uint32_t)ntl;    // local (layer, tile) sequence n = l * ntl + k
+  int tr_n = 0;
+  (void)tr_n;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.slots; ++i) {
@@ -167,37 +194,49 @@ conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ C
       const int src = p.layer[l].src;
       const int kws = (l == 0) ? 0 : min(p.slots - 1, ntl - 1);      // boxes of layer l prefetched before its weights
       int tile = blockIdx.x;
+      uint32_t known = 0;     // bit j: the dependencies of local tile k + j are known to be satisfied
       for (int k = 0; k < ntl; ++k, ++n, tile += G) {
+        CH_TRACE(0, 0, n);
         if (k == kws) {
           if (l > 0) mbar_wait_wd(&bar_wfree, (uint32_t)(l - 1) & 1u);       // every MMA of layer l-1 has retired
           if (tc::elect_one()) {
-            tc::mbar_expect_tx(&bar_w, p.w_bytes);
+            tc::mbar_expect_tx(&bar_w, p.w_bytes + (uint32_t)p.NB * 4u);
             tc::bulk_load(p.layer[l].wpack, &bar_w, smemW, p.w_bytes);
+            tc::bulk_load(p.layer[l].bias, &bar_w, &bias_s[l & 3][0], (uint32_t)p.NB * 4u);
           }
           __syncwarp();
+          CH_TRACE(0, 3, n);
         }
         const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-        if (l > 0 && (k % 3) == 0) {
-          // tile-level dependency: the 3 x 3 tile neighbourhood (incl. the tile itself) has completed l layers.  Checked for
-          // THREE local tiles per L2 round trip (lanes 0-8 / 9-17 / 18-26): one acquire round trip per tile (~0.7 us) would
-          // make this warp the pacing stage.  The extra tiles' dependencies are layer-(l-1) tiles of other CTAs, which never
-          // wait for a layer-l tile, so batching cannot deadlock.
-          const int j = lane / 9, nbr = lane - j * 9;
-          const int dy = nbr / 3 - 1, dx = nbr - (nbr / 3) * 3 - 1;
-          const int tj = tile + j * G;
-          const int tyj = tj / p.tiles_x, txj = tj - tyj * p.tiles_x;
-          const int tiles_y = p.ntiles / p.tiles_x;
-          const int ny = tyj + dy, nx = txj + dx;
-          const bool need = lane < 27 && (k + j) < ntl && ny >= 0 && ny < tiles_y && nx >= 0 && nx < p.tiles_x;
-          const int* f = p.flags + (need ? ny * p.tiles_x + nx : 0);
-          uint32_t spins = 0;
-          while (true) {
-            const int v = need ? ld_acquire(f) : l;
-            if (__all_sync(0xffffffffu, v >= l)) break;
-            if (++spins > (1u << 24)) __trap();
+        if (l > 0) {
+          // Tile-level dependency: the 3 x 3 tile neighbourhood (incl. the tile itself) has completed l layers.  One poll
+          // round looks at THREE local tiles (lanes 0-8 / 9-17 / 18-26) and remembers which of the next two are already
+          // satisfied, so in steady state there is one L2 round trip per three tiles, yet tile k never waits for the
+          // dependencies of k+1 / k+2.  Polls are relaxed GPU-scope loads; one acquire fence once the tile is cleared.
+          if (!(known & 1u)) {
+            const int j = lane / 9, nbr = lane - j * 9;
+            const int dy = nbr / 3 - 1, dx = nbr - (nbr / 3) * 3 - 1;
+            const int tj = tile + j * G;
+            const int tyj = tj / p.tiles_x, txj = tj - tyj * p.tiles_x;
+            const int tiles_y = p.ntiles / p.tiles_x;
+            const int ny = tyj + dy, nx = txj + dx;
+            const bool need = lane < 27 && (k + j) < ntl && ny >= 0 && ny < tiles_y && nx >= 0 && nx < p.tiles_x;
+            const int* f = p.flags + (need ? ny * p.tiles_x + nx : 0);
+            uint32_t spins = 0;
+            while (true) {
+              const int v = need ? ld_relaxed(f) : l;
+              const uint32_t b = __ballot_sync(0xffffffffu, v >= l);
+              known = ((b & 0x1ffu) == 0x1ffu ? 1u : 0u) | (((b >> 9) & 0x1ffu) == 0x1ffu ? 2u : 0u) |
+                      (((b >> 18) & 0x1ffu) == 0x1ffu ? 4u : 0u);
+              if (known & 1u) break;
+              if (++spins > (1u << 24)) __trap();
+            }
+            __threadfence();                                   // acquire side of the flags' release stores
+            asm volatile("fence.proxy.async;" ::: "memory");   // ... and the data is read through the async proxy (TMA) next
           }
-          asm volatile("fence.proxy.async;" ::: "memory");   // acquired data is read through the async proxy (TMA) next
+          known >>= 1;
         }
+        CH_TRACE(0, 1, n);
         const int slot = (int)(n % (uint32_t)p.slots);
         const uint32_t ph = (n / (uint32_t)p.slots) & 1u;
         mbar_wait_wd(&bar_empty[slot], ph ^ 1u);
@@ -206,6 +245,7 @@ conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ C
           tc::tma_load_3d(&maps.ld[src], &bar_full[slot], smemA + (size_t)slot * CH_A_BYTES, 0, tx * CH_TW - 1, ty * CH_TH - 1);
         }
         __syncwarp();
+        CH_TRACE(0, 2, n);
       }
     }
   } else if (warp_u < 1 + CH_NMMA) {
@@ -220,14 +260,18 @@ conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ C
         bool first = true;
         for (int k = id; k < ntl; k += p.nmma) {
           const uint32_t n = (uint32_t)l * (uint32_t)ntl + (uint32_t)k;
+          CH_TRACE(1 + id, 0, n);
           if (first) {
             mbar_wait_wd(&bar_w, (uint32_t)l & 1u);            // this layer's weights are resident
             first = false;
           }
+          CH_TRACE(1 + id, 1, n);
           const uint32_t slot = n % (uint32_t)p.slots, ph = (n / (uint32_t)p.slots) & 1u;
           const uint32_t acc = n % (uint32_t)CH_NACC, accph = (n / (uint32_t)CH_NACC) & 1u;
           mbar_wait_wd(&bar_tempty[acc], accph ^ 1u);
+          CH_TRACE(1 + id, 2, n);
           mbar_wait_wd(&bar_full[slot], ph);
+          CH_TRACE(1 + id, 3, n);
           tc::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.NB;
           const uint64_t ad = adesc0 + (uint64_t)(slot * a_step);
@@ -248,6 +292,7 @@ conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ C
             tc::umma_commit(&bar_tfull[acc]);       // accumulator complete -> epilogue group acc % 3
           }
           __syncwarp();
+          CH_TRACE(1 + id, 4, n);
         }
         // this warp's share of layer l has been issued: bar_wfree completes once all issuers' MMAs of the layer retired
         if (tc::elect_one()) tc::umma_commit(&bar_wfree);
@@ -286,7 +331,7 @@ conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ C
       if (p.layer[l].res < 0) return false;
       const int tile = blockIdx.x + k * G;
       const int need = p.layer[l].res_need;
-      if (need > 0 && ld_acquire(p.flags + tile) < need) return false;
+      if (need > 0 && ld_relaxed(p.flags + tile) < need) return false;      // (the vectors below are L2 reads issued after this test)
       const uint8_t* r = res_ptr(l, tile);
 #pragma unroll
       for (int v = 0; v < 6; ++v)
@@ -308,6 +353,7 @@ conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ C
       rn_ok = try_fetch(n + CH_NGRP, rn);           // one tile ahead (conv_tc.cu: a prefetch issued later hides nothing)
 
       const uint32_t acc = n % (uint32_t)CH_NACC, accph = (n / (uint32_t)CH_NACC) & 1u;
+      if (q == 0) CH_TRACE(4 + grp, 0, n);
       if (q == 0 && pend_tile >= 0) {
         // never block on an accumulator while holding an unpublished flag (deadlock freedom for any tile count)
         const bool ready = __all_sync(0xffffffffu, tc::mbar_try_wait(&bar_tfull[acc], accph));
@@ -319,6 +365,7 @@ conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ C
       }
       mbar_wait_wd(&bar_tfull[acc], accph);
       tc::tc_fence_after();
+      if (q == 0) CH_TRACE(4 + grp, 1, n);
       if (has_res && !rp_ok) {                      // rare: the residual tile was not yet published one tile ago
         const uint8_t* r = res_ptr(l, tile);        // (now it is: this tile's box was loaded after flags[tile] >= l >= res_need)
 #pragma unroll
@@ -334,11 +381,12 @@ conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ C
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bar_tempty[acc]);        // accumulator back to the MMA warps before the arithmetic
+      if (q == 0) CH_TRACE(4 + grp, 2, n);
 
       const float pre_slope = L.pre_slope, post_slope = L.post_slope;
       const int act_pre = (pre_slope == 1.f) ? 0 : (pre_slope == 0.f ? 1 : 2);
       const int act_post = (post_slope == 1.f) ? 0 : (post_slope == 0.f ? 1 : 2);
-      const float4* bias4 = reinterpret_cast<const float4*>(L.bias);
+      const float4* bias4 = reinterpret_cast<const float4*>(&bias_s[l & 3][0]);
       uint32_t ob[3][8];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -346,7 +394,7 @@ conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ C
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 b4 = __ldg(bias4 + c * 4 + (j >> 2));
+          const float4 b4 = bias4[c * 4 + (j >> 2)];
           v[j] = __uint_as_float(r[c][j]) + b4.x;
           v[j + 1] = __uint_as_float(r[c][j + 1]) + b4.y;
           v[j + 2] = __uint_as_float(r[c][j + 2]) + b4.z;
@@ -380,11 +428,9 @@ conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ C
         for (int j = 0; j < 8; ++j) ob[c][j] = pack2h(v[2 * j], v[2 * j + 1], T());
       }
 
-      // the group's previous store: complete -> publish its flag; the staging tile is free again
-      if (q == 0 && pend_tile >= 0) {
-        if (lane == 0) publish(p.flags + pend_tile, pend_val);
-        pend_tile = -1;
-      }
+      if (q == 0) CH_TRACE(4 + grp, 3, n);
+      // the staging tile is free once the group's previous store has READ it (completion / publication comes later)
+      if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       group_bar(1 + grp);
       // staging tile = 128 pixel rows of 128 B, 16-byte chunk j of row m at chunk j ^ (m & 7)  (SWIZZLE_128B)
 #pragma unroll
@@ -395,14 +441,19 @@ conv_chain_kernel(const __grid_constant__ ChMaps maps, const __grid_constant__ C
       }
       tc::fence_proxy_async();                      // generic smem writes -> visible to the async proxy (TMA store)
       group_bar(1 + CH_NGRP + grp);
+      if (q == 0) CH_TRACE(4 + grp, 4, n);
       if (q == 0) {
         if (lane == 0) {
           const int tyy = tile / p.tiles_x, txx = tile - tyy * p.tiles_x;
           tma_store_3d(&maps.st[L.dst], stg, 0, txx * CH_TW, tyy * CH_TH);
+          // the PREVIOUS store of this group has had a whole iteration to complete: publish its flag now, off the other
+          // three warps' path (they are already waiting for / draining the next accumulator)
+          if (pend_tile >= 0) publish_prev(p.flags + pend_tile, pend_val);
         }
         pend_tile = tile;
         pend_val = l + 1;
         __syncwarp();
+        CH_TRACE(4 + grp, 5, n);
       }
     }
     if (q == 0 && pend_tile >= 0 && lane == 0) publish(p.flags + pend_tile, pend_val);
@@ -461,6 +512,8 @@ extern "C" int rv_conv_chain(const rv_conv_chain_desc* d, void* stream) {
   p.ksteps = (d->C + 15) / 16;
   p.w_bytes = 9u * (uint32_t)d->nb * 128u;
   p.flags = d->flags;
+  { const char* e = getenv("REFVSR_CHAIN_TRACE"); p.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+  { const char* e = getenv("REFVSR_CHAIN_TRACE_CTA"); p.trace_cta = e ? atoi(e) : 70; }
   const size_t fixed = 1024 + 2048 + (size_t)p.w_bytes + (size_t)CH_NGRP * CH_STG_BYTES;
   RV_REQUIRE((size_t)max_smem > fixed + 2 * (size_t)CH_A_BYTES, "rv_conv_chain: shared memory too small");
   p.slots = (int)std::min<size_t>(CH_MAXSLOTS, ((size_t)max_smem - fixed) / CH_A_BYTES);

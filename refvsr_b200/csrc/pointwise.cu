@@ -2,6 +2,8 @@
 // reference gather / affine resampling, confidence-map glue and the reconstruction tail.
 // Every kernel is NHWC with 16-byte vector accesses where the channel count allows it.
 // Arithmetic follows SURVEY.md appendix A (verified against torch 2.11 by oracle/refvsr_oracle.py).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rv {
@@ -367,6 +369,131 @@ __global__ void __launch_bounds__(256) warp_vec_kernel(const T* __restrict__ src
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// rv_warp3 : the three warps of one propagation step in ONE launch (RefVSR.py:216-220,256-260):
+//   feat (h,w,C), conf (h,w) with the LR flow, feat_UP (2h,2w,C) with the x2 bilinear (align_corners=True) * 2 flow.
+// One CTA = one 8 x 16 LR tile = 16 x 32 pixels of the 2x grid.  Phase 0 stages the LR flow tile (+1 halo) in shared
+// memory (one coalesced read of the flow for all three warps), phase 1 computes for every output pixel of the tile the four
+// corner offsets (clamped) and weights (zero outside the image) into shared memory, phase 2 is the branch-free 4-tap gather
+// with one thread per (pixel, 16-byte channel vector): coalesced along the NHWC channel axis, and - because the tile is 2-D -
+// the corner rows shared by vertically adjacent output pixels are fetched from L2 once per CTA (L1 hits), not once per row.
+// Same arithmetic as warp_kernel / warp_vec_kernel (bit-identical results).
+// ---------------------------------------------------------------------------------------------
+constexpr int W3_TH = 8, W3_TW = 16;
+
+__device__ __forceinline__ void warp_corner(float X, float Y, float fx, float fy, int Wo, int Ho, int Wi, int Hi, int Xi, int Yi,
+                                            float4& wq, int4& off) {
+  float gx = linspace_m1_1(Xi, Wo) + fx / (((float)Wi - 1.0f) / 2.0f);   // models/utils.py:36-43
+  float gy = linspace_m1_1(Yi, Ho) + fy / (((float)Hi - 1.0f) / 2.0f);
+  float px = ((gx + 1.f) * (float)Wi - 1.f) / 2.f;
+  float py = ((gy + 1.f) * (float)Hi - 1.f) / 2.f;
+  float xw = floorf(px), yn = floorf(py);
+  int ix = (int)xw, iy = (int)yn;
+  float xe = xw + 1.f, ys = yn + 1.f;
+  wq = make_float4((xe - px) * (ys - py), (px - xw) * (ys - py), (xe - px) * (py - yn), (px - xw) * (py - yn));
+  const bool x0ok = ix >= 0 && ix < Wi, x1ok = ix + 1 >= 0 && ix + 1 < Wi;
+  const bool y0ok = iy >= 0 && iy < Hi, y1ok = iy + 1 >= 0 && iy + 1 < Hi;
+  if (!(y0ok && x0ok)) wq.x = 0.f;
+  if (!(y0ok && x1ok)) wq.y = 0.f;
+  if (!(y1ok && x0ok)) wq.z = 0.f;
+  if (!(y1ok && x1ok)) wq.w = 0.f;
+  const int cx0 = clampi(ix, 0, Wi - 1), cx1 = clampi(ix + 1, 0, Wi - 1);
+  const int cy0 = clampi(iy, 0, Hi - 1), cy1 = clampi(iy + 1, 0, Hi - 1);
+  off = make_int4(cy0 * Wi + cx0, cy0 * Wi + cx1, cy1 * Wi + cx0, cy1 * Wi + cx1);
+  (void)X; (void)Y;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) warp3_kernel(const T* __restrict__ feat, const T* __restrict__ featUP,
+                                                    const float* __restrict__ conf, const float* __restrict__ flow, int h, int w,
+                                                    int C, T* __restrict__ o_feat, T* __restrict__ o_featUP,
+                                                    float* __restrict__ o_conf) {
+  constexpr int V = 16 / (int)sizeof(T);
+  constexpr int NLR = W3_TH * W3_TW, NUP = 4 * NLR;
+  __shared__ float2 s_flow[(W3_TH + 2) * (W3_TW + 2)];
+  __shared__ float4 s_w[NLR + NUP];
+  __shared__ int4 s_o[NLR + NUP];
+  const int tiles_x = (w + W3_TW - 1) / W3_TW;
+  const int ty0 = (blockIdx.x / tiles_x) * W3_TH, tx0 = (blockIdx.x % tiles_x) * W3_TW;
+  const int H2 = 2 * h, W2 = 2 * w;
+  // ---- phase 0: LR flow tile with a one-pixel halo (the x2 flow of a tile reads rows / columns ty0 - 1 .. ty0 + TH)
+  for (int i = threadIdx.x; i < (W3_TH + 2) * (W3_TW + 2); i += blockDim.x) {
+    const int yy = clampi(ty0 - 1 + i / (W3_TW + 2), 0, h - 1), xx = clampi(tx0 - 1 + i % (W3_TW + 2), 0, w - 1);
+    s_flow[i] = __ldg(reinterpret_cast<const float2*>(flow) + (size_t)yy * w + xx);
+  }
+  __syncthreads();
+  auto flow_at = [&](int yy, int xx) -> float2 {      // (yy, xx) within [ty0 - 1, ty0 + TH] x [tx0 - 1, tx0 + TW] after clamping
+    return s_flow[(clampi(yy, 0, h - 1) - (ty0 - 1)) * (W3_TW + 2) + (clampi(xx, 0, w - 1) - (tx0 - 1))];
+  };
+  // ---- phase 1: corner offsets + weights
+  for (int i = threadIdx.x; i < NLR + NUP; i += blockDim.x) {
+    float4 wq = make_float4(0.f, 0.f, 0.f, 0.f);
+    int4 off = make_int4(0, 0, 0, 0);
+    if (i < NLR) {
+      const int Y = ty0 + i / W3_TW, X = tx0 + i % W3_TW;
+      if (Y < h && X < w) {
+        const float2 f = flow_at(Y, X);
+        warp_corner(0.f, 0.f, f.x, f.y, w, h, w, h, X, Y, wq, off);
+      }
+    } else {
+      const int j = i - NLR;
+      const int Y = 2 * ty0 + j / (2 * W3_TW), X = 2 * tx0 + j % (2 * W3_TW);
+      if (Y < H2 && X < W2) {
+        int y0, y1, x0, x1;
+        float ly, lx;
+        const float sy = (H2 > 1) ? (float)(h - 1) / (float)(H2 - 1) : 0.f;      // F.interpolate(x2, bilinear, align_corners=True)
+        const float sx = (W2 > 1) ? (float)(w - 1) / (float)(W2 - 1) : 0.f;
+        bilin_src_ac(Y, sy, h, y0, y1, ly);
+        bilin_src_ac(X, sx, w, x0, x1, lx);
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const float2 a = flow_at(y0, x0), b = flow_at(y0, x1), c = flow_at(y1, x0), d = flow_at(y1, x1);
+        const float fx = (hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x)) * 2.0f;
+        const float fy = (hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y)) * 2.0f;
+        warp_corner(0.f, 0.f, fx, fy, W2, H2, W2, H2, X, Y, wq, off);
+      }
+    }
+    s_w[i] = wq;
+    s_o[i] = off;
+  }
+  __syncthreads();
+  // ---- phase 2: gathers.  item = (pixel, vector); the 2x feature first (largest), then the LR feature, then conf.
+  const int cv = C / V;
+  auto gather = [&](const T* __restrict__ src, T* __restrict__ dst, int pl0, int npl, int tw, int Y0, int X0, int Hh, int Ww) {
+    for (int it = threadIdx.x; it < npl * cv; it += blockDim.x) {
+      const int pl = it / cv, vc = it - pl * cv;
+      const int Y = Y0 + pl / tw, X = X0 + pl % tw;
+      if (Y >= Hh || X >= Ww) continue;
+      const float4 wq = s_w[pl0 + pl];
+      const int4 o = s_o[pl0 + pl];
+      const T* base = src + (size_t)vc * V;
+      const Vec<T, V> t0 = ldv<T, V>(base + (size_t)o.x * C), t1 = ldv<T, V>(base + (size_t)o.y * C),
+                      t2 = ldv<T, V>(base + (size_t)o.z * C), t3 = ldv<T, V>(base + (size_t)o.w * C);
+      Vec<T, V> r;
+#pragma unroll
+      for (int k = 0; k < V; ++k)
+        r.v[k] = from_f<T>(to_f(t0.v[k]) * wq.x + to_f(t1.v[k]) * wq.y + to_f(t2.v[k]) * wq.z + to_f(t3.v[k]) * wq.w);
+      stv<T, V>(dst + ((size_t)Y * Ww + X) * C + (size_t)vc * V, r);
+    }
+  };
+  gather(featUP, o_featUP, NLR, NUP, 2 * W3_TW, 2 * ty0, 2 * tx0, H2, W2);
+  gather(feat, o_feat, 0, NLR, W3_TW, ty0, tx0, h, w);
+  if (threadIdx.x < NLR) {
+    const int Y = ty0 + threadIdx.x / W3_TW, X = tx0 + threadIdx.x % W3_TW;
+    if (Y < h && X < w) {
+      const float4 wq = s_w[threadIdx.x];
+      const int4 o = s_o[threadIdx.x];
+      // same accumulation order as warp_kernel<float, 1> (taps nw, ne, sw, se added one by one)
+      float acc = 0.f;
+      acc += __ldg(conf + o.x) * wq.x;
+      acc += __ldg(conf + o.y) * wq.y;
+      acc += __ldg(conf + o.z) * wq.z;
+      acc += __ldg(conf + o.w) * wq.w;
+      o_conf[(size_t)Y * w + X] = acc;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // rv_patch_pack : one warp per pixel
 // ---------------------------------------------------------------------------------------------
@@ -496,6 +623,69 @@ __global__ void aligned_sample_kernel(const T* __restrict__ x, int h, int w, int
     o.v[k] = from_f<T>(g_lt * to_f(t_lt.v[k]) + g_rb * to_f(t_rb.v[k]) + g_lb * to_f(t_lb.v[k]) +
                        g_rt * to_f(t_rt.v[k]));
   stv<T, V>(out + (size_t)p * C + (size_t)vc * V, o);
+}
+
+
+// ks = 2 (every x4 model): 2-D tiles of 8 x 16 cells = 16 x 32 output pixels.  Phase 1 evaluates the affine sampling position
+// ONCE per output pixel (the per-thread version above recomputes sin / cos / floor / reflect for each of the C/8 channel
+// vectors of a pixel) into shared memory, phase 2 is the same branch-free 4-tap gather as warp3_kernel.  Same arithmetic.
+template <typename T>
+__global__ void __launch_bounds__(256) aligned_sample2_kernel(const T* __restrict__ x, int h, int w, int C,
+                                                              const float* __restrict__ affine, T* __restrict__ out) {
+  constexpr int V = 16 / (int)sizeof(T);
+  constexpr int ks = 2, NP = 4 * W3_TH * W3_TW;
+  __shared__ float4 s_w[NP];
+  __shared__ int4 s_o[NP];
+  const int H = ks * h, W = ks * w, Hp = H + 2, Wp = W + 2;
+  const int tiles_x = (w + W3_TW - 1) / W3_TW;
+  const int Y0 = 2 * (blockIdx.x / tiles_x) * W3_TH, X0 = 2 * (blockIdx.x % tiles_x) * W3_TW;
+  for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+    const int Y = Y0 + i / (2 * W3_TW), X = X0 + i % (2 * W3_TW);
+    float4 wq = make_float4(0.f, 0.f, 0.f, 0.f);
+    int4 off = make_int4(0, 0, 0, 0);
+    if (Y < H && X < W) {
+      const int ci = Y / ks, a = Y % ks, cj = X / ks, b = X % ks;
+      const float* af = affine + ((size_t)ci * w + cj) * 3;
+      float s_x = af[0], s_y = af[1], th = (af[2] - 1.0f) * 1.0472f;
+      float half = (float)((ks - 1) / 2) + 0.5f;
+      float u = ((float)a - half) * s_x, v = ((float)b - half) * s_y;
+      float cs = cosf(th), sn = sinf(th);
+      float rr = u * cs - v * sn, cc = u * sn + v * cs;
+      float pr = rr + half + (float)(1 + ci * ks);
+      float pc = cc + half + (float)(1 + cj * ks);
+      float ltr = floorf(pr), ltc = floorf(pc);
+      float rbr = ltr + 1.f, rbc = ltc + 1.f;
+      const float Hm = (float)(Hp - 1), Wm = (float)(Wp - 1);
+      ltr = fminf(fmaxf(ltr, 0.f), Hm); rbr = fminf(fmaxf(rbr, 0.f), Hm);
+      ltc = fminf(fmaxf(ltc, 0.f), Wm); rbc = fminf(fmaxf(rbc, 0.f), Wm);
+      pr = fminf(fmaxf(pr, 0.f), Hm); pc = fminf(fmaxf(pc, 0.f), Wm);
+      // order (lt, rb, lb, rt) as in aligned_sample_kernel
+      wq = make_float4((1.f + (ltr - pr)) * (1.f + (ltc - pc)), (1.f - (rbr - pr)) * (1.f - (rbc - pc)),
+                       (1.f + (ltr - pr)) * (1.f - (rbc - pc)), (1.f - (rbr - pr)) * (1.f + (ltc - pc)));
+      const int r0 = reflect1((int)ltr - 1, H), r1 = reflect1((int)rbr - 1, H);
+      const int c0 = reflect1((int)ltc - 1, W), c1 = reflect1((int)rbc - 1, W);
+      off = make_int4(r0 * W + c0, r1 * W + c1, r0 * W + c1, r1 * W + c0);
+    }
+    s_w[i] = wq;
+    s_o[i] = off;
+  }
+  __syncthreads();
+  const int cv = C / V;
+  for (int it = threadIdx.x; it < NP * cv; it += blockDim.x) {
+    const int pl = it / cv, vc = it - pl * cv;
+    const int Y = Y0 + pl / (2 * W3_TW), X = X0 + pl % (2 * W3_TW);
+    if (Y >= H || X >= W) continue;
+    const float4 g = s_w[pl];
+    const int4 o = s_o[pl];
+    const T* base = x + (size_t)vc * V;
+    const Vec<T, V> t_lt = ldv<T, V>(base + (size_t)o.x * C), t_rb = ldv<T, V>(base + (size_t)o.y * C),
+                    t_lb = ldv<T, V>(base + (size_t)o.z * C), t_rt = ldv<T, V>(base + (size_t)o.w * C);
+    Vec<T, V> r;
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+      r.v[k] = from_f<T>(g.x * to_f(t_lt.v[k]) + g.y * to_f(t_rb.v[k]) + g.z * to_f(t_lb.v[k]) + g.w * to_f(t_rt.v[k]));
+    stv<T, V>(out + ((size_t)Y * W + X) * C + (size_t)vc * V, r);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -636,6 +826,75 @@ __global__ void frames_differ_kernel(const CmpPairs P, int* __restrict__ flag) {
   if (__any_sync(0xffffffffu, diff) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
+
+// x4 fast path: one thread per LR pixel produces its 4 x 4 output pixels.  The 16 outputs share one 5 x 5 LR neighbourhood
+// (the per-output version re-reads 16 taps per output pixel and channel); the four horizontal phases are evaluated once per
+// neighbourhood row (separable), conv_last's output is read as one 16-byte vector per pixel and each thread writes 16-byte
+// vectors of the planar result.  Weights, tap order and summation order are those of bicubic_planar (bit-identical).
+__global__ void __launch_bounds__(128) reconstruct4_kernel(const float4* __restrict__ x, const float* __restrict__ lr, int h, int w,
+                                                           int clamp01, float* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= h * w) return;
+  const int ly = p / w, lx = p - ly * w;
+  const int Ho = 4 * h, Wo = 4 * w;
+  float wt[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const float r = 0.25f * ((float)a + 0.5f) - 0.5f;          // fractional part of the source coordinate of phase a
+    cubic_weights(r - floorf(r), wt[a]);
+  }
+  int ry[5], rx[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { ry[i] = clampi(ly - 2 + i, 0, h - 1); rx[i] = clampi(lx - 2 + i, 0, w - 1); }
+  float res[3][4][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* s = lr + (size_t)c * h * w;
+    float hrow[4][5];                                          // [phase b][neighbourhood row]
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const float* r = s + (size_t)ry[i] * w;
+      const float v0 = __ldg(r + rx[0]), v1 = __ldg(r + rx[1]), v2 = __ldg(r + rx[2]), v3 = __ldg(r + rx[3]), v4 = __ldg(r + rx[4]);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        // phases 0, 1 look left (taps lx-2 .. lx+1), phases 2, 3 look right (lx-1 .. lx+2)
+        hrow[b][i] = (b < 2) ? (wt[b][0] * v0 + wt[b][1] * v1 + wt[b][2] * v2 + wt[b][3] * v3)
+                             : (wt[b][0] * v1 + wt[b][1] * v2 + wt[b][2] * v3 + wt[b][3] * v4);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int r0 = (a < 2) ? 0 : 1;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc += wt[a][j] * hrow[b][r0 + j];
+        res[c][a][b] = fminf(fmaxf(acc, 0.f), 1.f);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const size_t row = (size_t)(4 * ly + a) * Wo + 4 * lx;
+    float4 xv[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) xv[b] = __ldg(x + row + b);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float o[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const float xr = (c == 0) ? xv[b].x : (c == 1 ? xv[b].y : xv[b].z);
+        float v = xr + res[c][a][b];
+        if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+        o[b] = v;
+      }
+      *reinterpret_cast<float4*>(out + (size_t)c * Ho * Wo + row) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 }  // namespace rv
 
 // =================================================================================================
@@ -738,6 +997,23 @@ extern "C" int rv_warp(const void* src, int Hi, int Wi, int C, int dtype, const 
   return RV_OK;
 }
 
+extern "C" int rv_warp3(const void* feat, const void* featUP, const float* conf, const float* flow, int h, int w, int C,
+                        int dtype, void* out_feat, void* out_featUP, float* out_conf, void* stream) {
+  RV_REQUIRE(feat && featUP && conf && flow && out_feat && out_featUP && out_conf && h > 0 && w > 0, "rv_warp3: bad arguments");
+  RV_REQUIRE(dtype == RV_F16 || dtype == RV_BF16, "rv_warp3: f16 / bf16 features only (use rv_warp for fp32)");
+  RV_REQUIRE(C > 0 && C % 8 == 0, "rv_warp3: C=%d must be a multiple of 8", C);
+  const int tiles = ((h + W3_TH - 1) / W3_TH) * ((w + W3_TW - 1) / W3_TW);
+  if (dtype == RV_F16)
+    warp3_kernel<__half><<<tiles, 256, 0, (cudaStream_t)stream>>>((const __half*)feat, (const __half*)featUP, conf, flow, h, w, C,
+                                                                    (__half*)out_feat, (__half*)out_featUP, out_conf);
+  else
+    warp3_kernel<__nv_bfloat16><<<tiles, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)feat, (const __nv_bfloat16*)featUP, conf,
+                                                                           flow, h, w, C, (__nv_bfloat16*)out_feat,
+                                                                           (__nv_bfloat16*)out_featUP, out_conf);
+  RV_LAUNCH_CHECK("warp3");
+  return RV_OK;
+}
+
 extern "C" int rv_patch_pack(const void* feat, int H, int W, int C, int dtype, int mode, void* out,
                              int kpad, void* stream) {
   RV_REQUIRE(feat && out && H >= 2 && W >= 2, "rv_patch_pack: bad arguments");
@@ -777,7 +1053,10 @@ static int aligned_sample_launch(const void* x, int h, int w, int ks, int C, con
   constexpr int VMAX = 16 / sizeof(T);
   long long px = (long long)ks * h * ks * w;
   bool a16 = ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
-  if (C % VMAX == 0 && a16)
+  static const bool fast_ok = getenv("REFVSR_NO_FAST_POINTWISE") == nullptr;
+  if (fast_ok && ks == 2 && C % VMAX == 0 && a16)
+    aligned_sample2_kernel<T><<<((h + W3_TH - 1) / W3_TH) * ((w + W3_TW - 1) / W3_TW), 256, 0, st>>>((const T*)x, h, w, C, affine, (T*)out);
+  else if (C % VMAX == 0 && a16)
     aligned_sample_kernel<T, VMAX><<<cdiv(px * (C / VMAX), 256), 256, 0, st>>>((const T*)x, h, w, ks, C, affine, (T*)out);
   else
     aligned_sample_kernel<T, 1><<<cdiv(px * C, 256), 256, 0, st>>>((const T*)x, h, w, ks, C, affine, (T*)out);
@@ -854,8 +1133,13 @@ extern "C" int rv_reconstruct(const void* x, int xc, int x_dtype, const float* l
   RV_REQUIRE(x && lr && out && h > 0 && w > 0 && xc >= 3 && (scale == 2 || scale == 4),
              "rv_reconstruct: bad arguments");
   long long n = (long long)scale * h * scale * w;
-  RV_DISPATCH_DTYPE(x_dtype, T, (reconstruct_kernel<T><<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
-                                    (const T*)x, xc, lr, h, w, scale, clamp01, out)));
+  static const bool fast_ok = getenv("REFVSR_NO_FAST_POINTWISE") == nullptr;
+  if (fast_ok && scale == 4 && x_dtype == RV_F32 && xc == 4 && (uintptr_t)x % 16 == 0 && (uintptr_t)out % 16 == 0) {
+    reconstruct4_kernel<<<cdiv((long long)h * w, 128), 128, 0, (cudaStream_t)stream>>>((const float4*)x, lr, h, w, clamp01, out);
+  } else {
+    RV_DISPATCH_DTYPE(x_dtype, T, (reconstruct_kernel<T><<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      (const T*)x, xc, lr, h, w, scale, clamp01, out)));
+  }
   RV_LAUNCH_CHECK("reconstruct");
   return RV_OK;
 }

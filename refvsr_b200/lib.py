@@ -75,6 +75,7 @@ SIGNATURES = {
     'rv_spynet_level_input': (_I, [_P, _P, _P, _I, _I, _P, _I, _P, _P]),
     'rv_flow_resize': (_I, [_P, _I, _I, _P, _I, _I, _P]),
     'rv_warp': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
+    'rv_warp3': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     'rv_patch_pack': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     'rv_match_argmax': (_I, [_P, _I, _P, _I, _I, _F, _P, _P, _I, _P]),
     'rv_gather_blocks': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
@@ -275,6 +276,15 @@ class CudaOps:
             Hi, Wi, Cc = src.shape
         _check(self.lib, self.lib.rv_warp(_ptr(src), Hi, Wi, Cc, DTYPE_CODE[src.dtype], _ptr(flow), flow.shape[0],
                                           flow.shape[1], int(flow_up2), _ptr(out), self._stream()), 'rv_warp')
+
+    def warp3(self, feat, featUP, conf, flow, out_feat, out_featUP, out_conf):
+        """the three warps of one propagation step in one launch (16-bit features)"""
+        _chk_dev(feat, featUP, conf, flow, out_feat, out_featUP, out_conf)
+        h, w, Cc = feat.shape
+        assert tuple(featUP.shape) == (2 * h, 2 * w, Cc) and tuple(conf.shape) == (h, w) and tuple(flow.shape) == (h, w, 2)
+        assert feat.dtype == featUP.dtype == out_feat.dtype == out_featUP.dtype and conf.dtype == torch.float32
+        _check(self.lib, self.lib.rv_warp3(_ptr(feat), _ptr(featUP), _ptr(conf), _ptr(flow), h, w, Cc, DTYPE_CODE[feat.dtype],
+                                           _ptr(out_feat), _ptr(out_featUP), _ptr(out_conf), self._stream()), 'rv_warp3')
 
     # -- matching ---------------------------------------------------------------------------------
     def patch_pack(self, feat, out, mode):

@@ -89,8 +89,10 @@ class Network(nn.Module):
         # profiles/r01_conv_knockout.md) -> opt-in
         self.fuse_resblocks = bool(_cget(config, 'b200_fuse_resblocks', False))
         # cross-layer persistent chain kernel (rv_conv_chain): the 60-conv propagation trunks and the ResList decoders as ONE
-        # launch each, bit-identical to the per-layer path (csrc/conv_chain.cu)
-        self.use_chain = bool(_cget(config, 'b200_conv_chain', True)) and not os.environ.get('REFVSR_NO_CHAIN')   # (env: A/B runs)
+        # launch each, bit-identical to the per-layer path (csrc/conv_chain.cu).  Measured SLOWER than per-layer launches on
+        # B200 (20 vs 9.8 us per LR layer: per-tile GPU-scope synchronisation costs more than a launch boundary,
+        # profiles/r02_conv_chain.md) -> opt-in.
+        self.use_chain = bool(_cget(config, 'b200_conv_chain', False)) and not os.environ.get('REFVSR_NO_CHAIN')
         self.chain_max_ctas = int(_cget(config, 'b200_chain_max_ctas', 0))   # see rv_conv_chain_desc.max_ctas (dist.py sets it)
         self._ring_mod = None
         self._shard = None
@@ -724,6 +726,9 @@ class Network(nn.Module):
             return False
         return True
 
+    def _warp3_ok(self):
+        return self.act_dtype != torch.float32 and hasattr(self.ops, 'warp3') and not os.environ.get('REFVSR_NO_WARP3')
+
     def _backward_branch(self, a0, t, h, w, vis=None):
         """backward branch of the window at stream position a0 (RefVSR.py:211-238): window-local, starts from zeros at the
         window's last frame -> (feat_prop_UP, conf_map_prop) buffers at the centre frame"""
@@ -737,11 +742,14 @@ class Network(nn.Module):
             if i < t - 1:
                 flow = self._ring('bw', a0 + i, t, (h, w, 2))
                 wf = self._buf('bw.w.feat', (h, w, C), dt)
-                ops.warp(feat_prop, flow, wf)
                 wc = self._buf('bw.w.conf', (h, w), torch.float32)
-                ops.warp(conf_prop, flow, wc)
                 wu = self._buf('bw.w.featUP', (2 * h, 2 * w, C), dt)
-                ops.warp(feat_prop_UP, flow, wu, flow_up2=True)                # RefVSR.py:220
+                if self._warp3_ok():
+                    ops.warp3(feat_prop, feat_prop_UP, conf_prop, flow, wf, wu, wc)     # one launch, one flow read
+                else:
+                    ops.warp(feat_prop, flow, wf)
+                    ops.warp(conf_prop, flow, wc)
+                    ops.warp(feat_prop_UP, flow, wu, flow_up2=True)            # RefVSR.py:220
                 feat_prop, conf_prop, feat_prop_UP = wf, wc, wu
                 if vis is not None and i == mid:
                     vis['vis']['BW_LR_next_warp'] = self._warp_image(self._ring('lr32', a0 + i + 1, t, (3, h, w)), flow)
@@ -765,11 +773,14 @@ class Network(nn.Module):
         else:
             feat, featUP, conf = state
             wf = self._buf('fw.w.feat', (h, w, C), dt)
-            ops.warp(feat, flow, wf)
             wu = self._buf('fw.w.featUP', (2 * h, 2 * w, C), dt)
-            ops.warp(wf if quirk else featUP, flow, wu, flow_up2=True)
             wc = self._buf('fw.w.conf', (h, w), torch.float32)
-            ops.warp(conf, flow, wc)
+            if not quirk and self._warp3_ok():
+                ops.warp3(feat, featUP, conf, flow, wf, wu, wc)
+            else:
+                ops.warp(feat, flow, wf)
+                ops.warp(wf if quirk else featUP, flow, wu, flow_up2=True)
+                ops.warp(conf, flow, wc)
             feat_prop, feat_prop_UP, conf_prop = wf, wu, wc
         fp = self._frame_slot(a % self._rm(t), h, w)
         agg = self._prop_resblocks('forward_resblocks', fp['lr8'], feat_prop, self._buf('fw.agg', (h, w, C), dt), 'fw.rb')

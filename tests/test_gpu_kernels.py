@@ -512,3 +512,24 @@ def test_conv_chain_more_than_64_layers_and_errors(cuda_ops):
     assert torch.equal(bufs[out_idx], expect)
     with pytest.raises(ValueError, match='own source'):
         cuda_ops.conv_chain(bufs, [(chain_l[0], 0, -1, 0, 0, 0)], flags)
+
+
+@pytest.mark.parametrize('prec', ['fp16', 'bf16'])
+@pytest.mark.parametrize('h,w,C', [(24, 40, 48), (37, 53, 24), (270, 480, 48)])
+def test_warp3_equals_three_warps(cuda_ops, prec, h, w, C):
+    """rv_warp3 (one launch, one flow read, 2-D tiles) is bit-identical to the three rv_warp launches it replaces"""
+    dt = DT[prec]
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn((h, w, C), generator=g).to(dt).cuda()
+    featUP = torch.randn((2 * h, 2 * w, C), generator=g).to(dt).cuda()
+    conf = torch.rand((h, w), generator=g).cuda()
+    flow = (torch.randn((h, w, 2), generator=g) * 3.0).cuda()
+    flow[:4] *= 20.0                                       # some taps far outside the image (zeros padding)
+    e_f, e_u, e_c = torch.empty_like(feat), torch.empty_like(featUP), torch.empty_like(conf)
+    cuda_ops.warp(feat, flow, e_f)
+    cuda_ops.warp(conf, flow, e_c)
+    cuda_ops.warp(featUP, flow, e_u, flow_up2=True)
+    o_f, o_u, o_c = torch.full_like(feat, float('nan')), torch.full_like(featUP, float('nan')), torch.full_like(conf, float('nan'))
+    cuda_ops.warp3(feat, featUP, conf, flow, o_f, o_u, o_c)
+    torch.cuda.synchronize()
+    assert torch.equal(o_f, e_f) and torch.equal(o_u, e_u) and torch.equal(o_c, e_c)
