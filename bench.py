@@ -196,6 +196,16 @@ def kernel_rooflines(net, peaks):
     byt = 2.0 * 4 * H * W * C * e + 8.0 * H * W
     out['warp_up'] = dict(bound='hbm', achieved=byt / twarp / 1e9, peak=peaks['hbm'], unit='GB/s',
                           frac=byt / twarp / 1e9 / peaks['hbm'], seconds=twarp, algorithmic_bytes=byt)
+    if dt != torch.float32 and hasattr(ops, 'warp3'):
+        # fused K1: feat + conf + feat_UP of one propagation step from ONE flow read ((10C+4)P elements)
+        lf = [torch.randn((H, W, C), device=dev).to(dt) for _ in range(nrot2)]
+        lo = [torch.empty((H, W, C), device=dev, dtype=dt) for _ in range(nrot2)]
+        cf, co = torch.rand((H, W), device=dev), torch.empty((H, W), device=dev)
+        tw3 = timeit(lambda i: ops.warp3(lf[i % nrot2], fs[i % nrot2], cf, flow, lo[i % nrot2], fo[i % nrot2], co))
+        byt3 = 2.0 * 5 * H * W * C * e + 2.0 * 4 * H * W + 8.0 * H * W
+        out['warp3'] = dict(bound='hbm', achieved=byt3 / tw3 / 1e9, peak=peaks['hbm'], unit='GB/s', frac=byt3 / tw3 / 1e9 / peaks['hbm'],
+                            seconds=tw3, algorithmic_bytes=byt3)
+        del lf, lo
     # the same trunk as ONE persistent launch (rv_conv_chain): 30 residual blocks = 60 convs over L2-resident ping-pong maps
     if dt != torch.float32 and hasattr(ops, 'conv_chain') and C <= 48:          # (opt-in kernel, reported as evidence)
         from refvsr_b200.lib import ACT_NONE

@@ -206,7 +206,7 @@ int rv_warp(const void* src, int Hi, int Wi, int C, int dtype, const float* flow
 /* The three warps of one propagation step fused into ONE launch (RefVSR.py:216-220 backward branch, :256-260 steady forward
  * step): out_feat = warp(feat, flow), out_conf = warp(conf, flow), out_featUP = warp(featUP, interpolate(flow, x2, bilinear,
  * align_corners=True) * 2).  feat (h,w,C), featUP (2h,2w,C) f16/bf16, conf (h,w) fp32, flow (h,w,2) fp32.  The flow is read
- * once; results are bit-identical to three rv_warp calls.  (Not for the first-window quirk RefVSR.py:252-254, whose 2x warp
+ * once; same arithmetic as three rv_warp calls (feat / conf bit-identical, featUP to the last bit of the storage type).  (Not for the first-window quirk RefVSR.py:252-254, whose 2x warp
  * reads the OUTPUT of the LR warp.) */
 int rv_warp3(const void* feat, const void* featUP, const float* conf, const float* flow, int h, int w, int C, int dtype,
              void* out_feat, void* out_featUP, float* out_conf, void* stream);

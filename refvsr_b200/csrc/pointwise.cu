@@ -460,20 +460,30 @@ __global__ void __launch_bounds__(256) warp3_kernel(const T* __restrict__ feat, 
   // ---- phase 2: gathers.  item = (pixel, vector); the 2x feature first (largest), then the LR feature, then conf.
   const int cv = C / V;
   auto gather = [&](const T* __restrict__ src, T* __restrict__ dst, int pl0, int npl, int tw, int Y0, int X0, int Hh, int Ww) {
-    for (int it = threadIdx.x; it < npl * cv; it += blockDim.x) {
-      const int pl = it / cv, vc = it - pl * cv;
-      const int Y = Y0 + pl / tw, X = X0 + pl % tw;
-      if (Y >= Hh || X >= Ww) continue;
-      const float4 wq = s_w[pl0 + pl];
-      const int4 o = s_o[pl0 + pl];
-      const T* base = src + (size_t)vc * V;
-      const Vec<T, V> t0 = ldv<T, V>(base + (size_t)o.x * C), t1 = ldv<T, V>(base + (size_t)o.y * C),
-                      t2 = ldv<T, V>(base + (size_t)o.z * C), t3 = ldv<T, V>(base + (size_t)o.w * C);
-      Vec<T, V> r;
+    // two (pixel, vector) items per thread and iteration: all eight 16-byte loads are issued before the first use
+    const int nit = npl * cv;
+    for (int it = threadIdx.x; it < nit; it += 2 * blockDim.x) {
+      const int itb = it + blockDim.x;
+      const int pla = it / cv, vca = it - pla * cv;
+      const int plb = (itb < nit) ? itb / cv : pla, vcb = (itb < nit) ? itb - plb * cv : vca;
+      const int Ya = Y0 + pla / tw, Xa = X0 + pla % tw, Yb = Y0 + plb / tw, Xb = X0 + plb % tw;
+      const bool oka = Ya < Hh && Xa < Ww, okb = itb < nit && Yb < Hh && Xb < Ww;
+      const float4 wa = s_w[pl0 + pla], wb = s_w[pl0 + plb];
+      const int4 oa = s_o[pl0 + pla], ob = s_o[pl0 + plb];            // (offsets of out-of-image pixels are 0: safe to read)
+      const T* ba = src + (size_t)vca * V;
+      const T* bb = src + (size_t)vcb * V;
+      const Vec<T, V> a0 = ldv<T, V>(ba + (size_t)oa.x * C), a1 = ldv<T, V>(ba + (size_t)oa.y * C),
+                      a2 = ldv<T, V>(ba + (size_t)oa.z * C), a3 = ldv<T, V>(ba + (size_t)oa.w * C);
+      const Vec<T, V> b0 = ldv<T, V>(bb + (size_t)ob.x * C), b1 = ldv<T, V>(bb + (size_t)ob.y * C),
+                      b2 = ldv<T, V>(bb + (size_t)ob.z * C), b3 = ldv<T, V>(bb + (size_t)ob.w * C);
+      Vec<T, V> ra, rb;
 #pragma unroll
-      for (int k = 0; k < V; ++k)
-        r.v[k] = from_f<T>(to_f(t0.v[k]) * wq.x + to_f(t1.v[k]) * wq.y + to_f(t2.v[k]) * wq.z + to_f(t3.v[k]) * wq.w);
-      stv<T, V>(dst + ((size_t)Y * Ww + X) * C + (size_t)vc * V, r);
+      for (int k = 0; k < V; ++k) {
+        ra.v[k] = from_f<T>(to_f(a0.v[k]) * wa.x + to_f(a1.v[k]) * wa.y + to_f(a2.v[k]) * wa.z + to_f(a3.v[k]) * wa.w);
+        rb.v[k] = from_f<T>(to_f(b0.v[k]) * wb.x + to_f(b1.v[k]) * wb.y + to_f(b2.v[k]) * wb.z + to_f(b3.v[k]) * wb.w);
+      }
+      if (oka) stv<T, V>(dst + ((size_t)Ya * Ww + Xa) * C + (size_t)vca * V, ra);
+      if (okb) stv<T, V>(dst + ((size_t)Yb * Ww + Xb) * C + (size_t)vcb * V, rb);
     }
   };
   gather(featUP, o_featUP, NLR, NUP, 2 * W3_TW, 2 * ty0, 2 * tx0, H2, W2);

@@ -24,7 +24,10 @@ METRICS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.
 # algorithmic bytes / flops per launch at the captured shapes (bench.kernel_rooflines), peak 6575 GB/s / 1705 TF/s
 ALGO = {
     'warp_vec': ('hbm', 100.6e6, 'K1 flow warp of the (2h, 2w, C) feature with the x2 flow upsample fused'),
-    'warp3': ('hbm', 125.5e6, 'K1 fused warp of feat + conf + feat_UP from one flow read'),
+    'warp3': ('hbm', 126.5e6, 'K1 fused warp of feat + conf + feat_UP from one flow read'),
+    'aligned_sample2': ('hbm', 101.1e6, 'K4 AlignedConv2d resampling, tiled kernel (ks = 2)'),
+    'reconstruct4': ('hbm', 59.6e6, 'K7 conv_last output + bicubic x4 base + clamp, one thread per LR pixel'),
+    'match_tc': ('tensor', 1.209e12, 'K2 matching GEMM + argmax, single pass (default mode)'),
     'gather_blocks': ('hbm', 25.4e6, 'K3 aa1 gather (first gather_blocks launch of profile_kernels.py)'),
     'aligned_sample': ('hbm', 101.1e6, 'K4 AlignedConv2d resampling of the gathered 2x feature'),
     'reconstruct': ('hbm', 59.6e6, 'K7 conv_last output + bicubic x4 base + clamp'),
