@@ -864,6 +864,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   RV_MARK(2);
 }
 
+#ifdef RV_WATCHDOG
+}  // namespace rv
+extern "C" int rv_set_watchdog_buffer(void* host_mapped) {
+  unsigned long long* p = (unsigned long long*)host_mapped;
+  return cudaMemcpyToSymbol(rv::tc::rv_wd_buf, &p, sizeof(p)) == cudaSuccess ? 0 : -2;
+}
+namespace rv {
+#endif
+
 PFN_tmapEncodeTiled get_tmap_encoder() {
   static PFN_tmapEncodeTiled fn = nullptr;
   static bool tried = false;
@@ -1053,6 +1062,16 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   // (an issuer further ahead than the shared-memory ring would alias mbarrier phases, so this is a hard limit)
   p.nmma = std::max(1, std::min(std::min((int)MAX_MMA, p.slots * p.grp / p.S), p.nacc));
   if (nmma_env > 0) p.nmma = std::min(p.nmma, nmma_env);
+  {
+    // KNOWN ISSUE (round 2, profiles/r02_8k.md): with more than one issuing warp, launches whose CTAs walk hundreds of tiles
+    // (1080x1920 and larger maps: the flag_HD_in "8K" configs) dead-lock once in ~20 launches - watchdog dumps show every
+    // issuer waiting for a box while the producer waits for the previous occupant of its next slot, i.e. a tcgen05.commit
+    // arrival that never lands.  Not reproduced at <= 60 tiles per CTA (400 repetitions at 540x960).  Until the root cause is
+    // understood such launches use ONE issuing warp (measured correct: 60 repetitions per shape, full 8K windows).
+    const int ntiles_ = ((p.Wo + p.tw - 1) / p.tw) * ((p.Ho + p.th - 1) / p.th);
+    const int per_cta = ntiles_ / std::max(1, std::min(ntiles_, std::max(1, g_num_sms / nblk)));
+    if (per_cta > 64) p.nmma = 1;
+  }
   while (cols < (uint32_t)p.nacc * p.acc_stride) cols <<= 1;
   p.tmem_cols = cols;
 

@@ -3,6 +3,7 @@
 // Bit layouts follow the PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor" tables
 // (same fields as cute/arch/mma_sm100_desc.hpp in CUTLASS 4.x).
 #pragma once
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -44,6 +45,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // The spin loop lives INSIDE the asm block: a C++ `while (!try_wait)` is a divergent loop to the compiler, after which
 // it no longer treats warp-uniform values (UMMA descriptors, barrier addresses) as uniform.
+#ifdef RV_WATCHDOG
+// diagnostics build (tools/conv_big_probe.py): a wait that never completes records who waited on what in a pinned HOST buffer
+// (device printf output does not survive the trap), then aborts the launch.  One copy of the pointer per translation unit.
+static __device__ unsigned long long* rv_wd_buf = nullptr;
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return;
+    if (spins > (1u << 21)) {
+      if ((threadIdx.x & 31) == 0 && rv_wd_buf != nullptr) {
+        const unsigned long long i = atomicAdd(rv_wd_buf, 1ull);
+        if (i < 1000) {
+          rv_wd_buf[1 + i] = ((unsigned long long)blockIdx.x << 48) | ((unsigned long long)blockIdx.y << 40) |
+                             ((unsigned long long)(threadIdx.x >> 5) << 32) | ((unsigned long long)(smem_u32(bar) & 0xffffffu) << 8) | parity;
+        }
+        __threadfence_system();
+      }
+      __nanosleep(2000000);
+      __trap();
+    }
+  }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -55,6 +78,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+#endif
 
 // ---- TMA ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
