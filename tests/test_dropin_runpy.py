@@ -109,6 +109,21 @@ def test_run_py_eval_unmodified_vs_dropin_cpu(tmp_path):
     for (v, f, p0, s0), (_, _, p1, s1) in zip(base, ours):
         assert abs(p0 - p1) <= 1e-4 and abs(s0 - s1) <= 1e-5, f'video {v} frame {f}: PSNR {p0} vs {p1}, SSIM {s0} vs {s1}'
     assert '[TOTAL' in log
+    # the evaluation-loop drop-in (refvsr_b200/dropin/evaluation) writes the same image tree and score file as the reference's loop
+    import cv2
+
+    def tree(tag):
+        root = os.path.join(tmp, 'out_' + tag)
+        return {os.path.relpath(os.path.join(d, f), root).split(os.sep, 4)[-1] if False else
+                re.sub(r'/\d{4}_\d{2}_\d{2}_\d{4}/', '/DATE/', os.path.relpath(os.path.join(d, f), root)): os.path.join(d, f)
+                for d, _, fs in os.walk(root) for f in fs}
+    ta, tb = tree('ref'), tree('b200')
+    strip = lambda t, tag: {k.replace('dropin_' + tag, 'MODE'): v for k, v in t.items()}
+    ta, tb = strip(ta, 'ref'), strip(tb, 'b200')
+    assert set(ta) == set(tb) and sum(k.endswith('.png') for k in ta) == 12, sorted(set(ta) ^ set(tb))[:6]
+    for k in ta:
+        if k.endswith('.png'):
+            assert np.abs(cv2.imread(ta[k]).astype(int) - cv2.imread(tb[k]).astype(int)).max() <= 1, k
 
 
 @pytest.mark.gpu
