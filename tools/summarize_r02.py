@@ -31,7 +31,8 @@ ALGO = {
     'gather_blocks': ('hbm', 25.4e6, 'K3 aa1 gather (first gather_blocks launch of profile_kernels.py)'),
     'aligned_sample': ('hbm', 101.1e6, 'K4 AlignedConv2d resampling of the gathered 2x feature'),
     'reconstruct': ('hbm', 59.6e6, 'K7 conv_last output + bicubic x4 base + clamp'),
-    'conv_chain': ('tensor', 60 * 5.374e9, 'K5 60-layer trunk as one persistent launch'),
+    'conv_chain': ('tensor', 60 * 5.374e9, 'K5 60-layer trunk as one persistent launch (opt-in kernel)'),
+    'conv_tc': ('tensor', 5.374e9, 'K5 conv3x3 48->48 @270x480 +ReLU +residual, one launch (the roofline kernel of the bench line)'),
     'match': ('tensor', 1.209e12, 'K2 matching GEMM + argmax, single pass'),
 }
 UNIT = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
@@ -84,9 +85,10 @@ def kernels():
         js[key] = {'duration_us': t_us, 'traffic': traffic, 'kernel': d['kernel'][:120], **{m: d[m][0] for m in METRICS if m in d}}
     open(os.path.join(P, 'r02_ncu_kernels.md'), 'w').write('\n'.join(lines) + '\n')
     json.dump(js, open(os.path.join(P, 'r02_ncu_kernels.json'), 'w'), indent=1)
-    if 'conv_chain' in js:
-        json.dump({'traffic': js['conv_chain']['traffic'] / 60.0, 'note': 'dram bytes of the 60-layer rv_conv_chain launch / 60 layers',
-                   'duration_us_per_layer_cold': js['conv_chain']['duration_us'] / 60.0}, open(os.path.join(P, 'r02_ncu_conv_lr.json'), 'w'))
+    if 'conv_tc' in js:      # the bench line's roofline.traffic (dominant kernel: conv_tc 3x3 48->48 @270x480 +ReLU +residual)
+        json.dump({'traffic': js['conv_tc']['traffic'], 'duration_us_cold': js['conv_tc']['duration_us'],
+                   'note': 'dram__bytes_read.sum + dram__bytes_write.sum of ONE conv_tc launch (tools/ncu_conv.py under ncu --set full, round 2)'},
+                  open(os.path.join(P, 'r02_ncu_conv_lr.json'), 'w'))
 
 
 def launches(name, out):
