@@ -521,6 +521,9 @@ extern "C" int rv_conv_chain(const rv_conv_chain_desc* d, void* stream) {
   if (d->max_ctas > 0) grid = std::min(grid, (int)d->max_ctas);
   p.nmma = std::max(1, std::min(std::min(CH_NMMA, p.ntiles / grid), p.slots));
   { const char* e = getenv("REFVSR_CHAIN_NMMA"); if (e && atoi(e) > 0) p.nmma = std::min(p.nmma, atoi(e)); }
+  // every issuer must own its smem slots exclusively (mbarrier parity waits alias across issuers otherwise - conv_tc.cu): slots is
+  // a multiple of the issuer count; CH_NACC = 6 is a multiple of 1, 2 and 3
+  p.slots = (p.slots / p.nmma) * p.nmma;
   int last_write[CH_MAXB];
   for (int b = 0; b < CH_MAXB; ++b) { last_write[b] = 0; p.buf[b] = b < d->nbuf ? d->buf[b] : nullptr; }
   for (int l = 0; l < d->nlayers; ++l) {

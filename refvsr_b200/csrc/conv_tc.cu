@@ -1057,20 +1057,23 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   uint32_t cols = 32;
   // accumulator t % nacc must always belong to the same epilogue group (t % 3): nacc is 3 or 6
   p.nacc = (6 * p.acc_stride <= 512) ? 6 : 3;
-  // issuers: as many as there are whole tiles in flight in shared memory (and accumulators to write to)
+  // Issuers: as many as there are whole tiles in flight in shared memory (and accumulators to write to) - and every issuer
+  // must OWN its smem slots and accumulators.  All waits are mbarrier PARITY waits: a warp that waits for the k-th fill of a
+  // slot passes as soon as the barrier's completed-phase count has the right parity, i.e. also when it is still TWO fills
+  // short.  That cannot happen to the warp that consumed fill k-1 itself, but it does happen to ANOTHER issuer that reaches the
+  // slot `slots` tiles later while the earlier fill (a TMA box with a long-tail latency: cold DRAM page / TLB miss on a
+  // > 100 MB map) is still in flight - it then multiplies stale data, commits, and the barrier phases are off by two for good
+  // (round 2: 48 -> 192 pixel-shuffle conv at 1080x1920, 4 slots / 3 issuers, dead-lock in ~1 of 20 launches;
+  // profiles/r02_8k.md).  With tiles-in-flight and accumulators both multiples of the issuer count, consecutive uses of a slot /
+  // accumulator always belong to the same issuer and the parity wait is exact.
   static const int nmma_env = getenv("REFVSR_NMMA") ? atoi(getenv("REFVSR_NMMA")) : 0;
-  // (an issuer further ahead than the shared-memory ring would alias mbarrier phases, so this is a hard limit)
-  p.nmma = std::max(1, std::min(std::min((int)MAX_MMA, p.slots * p.grp / p.S), p.nacc));
-  if (nmma_env > 0) p.nmma = std::min(p.nmma, nmma_env);
   {
-    // KNOWN ISSUE (round 2, profiles/r02_8k.md): with more than one issuing warp, launches whose CTAs walk hundreds of tiles
-    // (1080x1920 and larger maps: the flag_HD_in "8K" configs) dead-lock once in ~20 launches - watchdog dumps show every
-    // issuer waiting for a box while the producer waits for the previous occupant of its next slot, i.e. a tcgen05.commit
-    // arrival that never lands.  Not reproduced at <= 60 tiles per CTA (400 repetitions at 540x960).  Until the root cause is
-    // understood such launches use ONE issuing warp (measured correct: 60 repetitions per shape, full 8K windows).
-    const int ntiles_ = ((p.Wo + p.tw - 1) / p.tw) * ((p.Ho + p.th - 1) / p.th);
-    const int per_cta = ntiles_ / std::max(1, std::min(ntiles_, std::max(1, g_num_sms / nblk)));
-    if (per_cta > 64) p.nmma = 1;
+    const int unit = (p.grp == p.S) ? 1 : p.S;                 // smem slots (barrier pairs) per tile
+    int tif = p.slots / unit;                                  // whole tiles in flight
+    p.nmma = std::max(1, std::min(std::min((int)MAX_MMA, tif), p.nacc));
+    if (nmma_env > 0) p.nmma = std::min(p.nmma, nmma_env);
+    while (p.nmma > 1 && (p.nacc % p.nmma != 0 || tif / p.nmma == 0)) --p.nmma;
+    if (p.nmma > 1) p.slots = (tif / p.nmma) * p.nmma * unit;     // (a single issuer keeps whatever ring it has, even < 1 tile)
   }
   while (cols < (uint32_t)p.nacc * p.acc_stride) cols <<= 1;
   p.tmem_cols = cols;
