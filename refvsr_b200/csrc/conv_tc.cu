@@ -57,6 +57,7 @@ struct TcP {
   int nacc;                               // accumulator buffers in TMEM (3 or 6)
   int fold;                               // mode 3: the 3 kx taps folded into N = 3 * NB (see conv_tc_kernel MODE 3)
   int fast;                               // streamlined epilogue (all-16-bit, vector stores, full 16-channel chunks)
+  int vlast;                              // 16-byte vectors of the LAST 16-column chunk that exist in memory (2, or 1 when cout = NB - 8)
   int nmma;                               // MMA-issuing warps in use (1..MAX_MMA), tiles dealt round-robin
   int grp;                                // consecutive stages that share one full/empty barrier pair (1 or S)
   int sw32, nq0, nq1;
@@ -472,7 +473,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
             if (c < nch) {
               const uint4* q4 = reinterpret_cast<const uint4*>(res + pix * p.res_cs + nbase + c * 16);
               dst[c][0] = __ldg(q4);
-              dst[c][1] = __ldg(q4 + 1);
+              dst[c][1] = (c + 1 < nch || p.vlast == 2) ? __ldg(q4 + 1) : make_uint4(0, 0, 0, 0);
             }
         }
       };
@@ -528,7 +529,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           }
           if (gate != nullptr) {
             const uint4* g4 = reinterpret_cast<const uint4*>(gate + pix * p.gate_cs + nbase + n0);
-            const uint4 ga = __ldg(g4), gb = __ldg(g4 + 1);
+            const uint4 ga = __ldg(g4), gb = (c + 1 < nch || p.vlast == 2) ? __ldg(g4 + 1) : make_uint4(0, 0, 0, 0);
             const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -542,7 +543,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
             if (c < 3) { ra = rp[c < 3 ? c : 0][0]; rb = rp[c < 3 ? c : 0][1]; }
             else {
               const uint4* q4 = reinterpret_cast<const uint4*>(res + pix * p.res_cs + nbase + n0);
-              ra = __ldg(q4); rb = __ldg(q4 + 1);
+              ra = __ldg(q4); rb = (c + 1 < nch || p.vlast == 2) ? __ldg(q4 + 1) : make_uint4(0, 0, 0, 0);
             }
             const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
@@ -569,7 +570,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
             o1.x = pack2(v[8], v[9], TO()); o1.y = pack2(v[10], v[11], TO()); o1.z = pack2(v[12], v[13], TO()); o1.w = pack2(v[14], v[15], TO());
             uint4* o = reinterpret_cast<uint4*>(out + pix * p.out_cs + nbase + n0);
             o[0] = o0;
-            o[1] = o1;
+            if (c + 1 < nch || p.vlast == 2) o[1] = o1;
           }
         }
         RV_TRACE(2 + grp, 3, tile);
@@ -603,7 +604,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
               if (c < nch) {
                 const uint4* q4 = reinterpret_cast<const uint4*>(res + pix * p.res_cs + nbase + c * 16);
                 dst[c][0] = __ldg(q4);
-                dst[c][1] = __ldg(q4 + 1);
+                dst[c][1] = (c + 1 < nch || p.vlast == 2) ? __ldg(q4 + 1) : make_uint4(0, 0, 0, 0);
               }
           }
         };
@@ -671,7 +672,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
               }
               if (gate != nullptr) {
                 const uint4* g4 = reinterpret_cast<const uint4*>(gate + pix * p.gate_cs + nbase + n0);
-                const uint4 ga = __ldg(g4), gb = __ldg(g4 + 1);
+                const uint4 ga = __ldg(g4), gb = (c3 + c + 1 < nch || p.vlast == 2) ? __ldg(g4 + 1) : make_uint4(0, 0, 0, 0);
                 const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -685,7 +686,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                 if (c3 == 0) { ra = rp[c][0]; rb = rp[c][1]; }
                 else {
                   const uint4* q4 = reinterpret_cast<const uint4*>(res + pix * p.res_cs + nbase + n0);
-                  ra = __ldg(q4); rb = __ldg(q4 + 1);
+                  ra = __ldg(q4); rb = (c3 + c + 1 < nch || p.vlast == 2) ? __ldg(q4 + 1) : make_uint4(0, 0, 0, 0);
                 }
                 const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
@@ -720,7 +721,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                   o1.x = pack2(v[8], v[9], TO()); o1.y = pack2(v[10], v[11], TO()); o1.z = pack2(v[12], v[13], TO()); o1.w = pack2(v[14], v[15], TO());
                   uint4* o = reinterpret_cast<uint4*>(out + pix * p.out_cs + nbase + n0);
                   o[0] = o0;
-                  o[1] = o1;
+                  if (c3 + c + 1 < nch || p.vlast == 2) o[1] = o1;
                 }
               }
             }
@@ -975,7 +976,12 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   static const bool fast_ok = getenv("REFVSR_NO_FAST_EPILOGUE") == nullptr;
   // (pixel-shuffle outputs: 8-byte stores of 4 channels, so (cout / 4) channels per pixel must keep them 8-byte aligned)
   const bool ps_ok = !d->pixel_shuffle || ((d->layout == 1 || d->layout == 3) && p.NB % 32 == 0 && p.NB <= 96 && (d->out_cs * 2) % 16 == 0 && d->res == nullptr && d->gate == nullptr && (d->out_cs * 2) % 8 == 0 && ((uintptr_t)d->out % 8) == 0);
-  p.fast = fast_ok && p.vec_ok && ps_ok && (d->cout % p.NB == 0) && d->out_dtype != RV_F32 && rdt != RV_F32 &&
+  // cout = NB - 8 with a single column block (the small models' 24-channel maps, NB = 32): the last chunk holds one 16-byte vector
+  // per pixel instead of two; the padding columns compute zeros (zero weights and bias) and are simply not stored / not read
+  const bool ragged_ok = (nblk == 1) && (d->cout == p.NB - 8) && !d->pixel_shuffle && d->out_cs == d->cout &&
+                         (!d->res || d->res_cs == d->cout) && (!d->gate || d->gate_cs == d->cout);
+  p.vlast = (d->cout % p.NB == 0) ? 2 : 1;
+  p.fast = fast_ok && p.vec_ok && ps_ok && (d->cout % p.NB == 0 || ragged_ok) && d->out_dtype != RV_F32 && rdt != RV_F32 &&
            d->out_dtype == d->in_dtype && rdt == d->in_dtype && (p.dbg & 31) == 0;   // knock-out bits 32/64/128 are fast-path experiments
   // mode 1 (single box per tile and chunk) when the whole weight set stays resident next to >= 2 boxes
   p.single_box = 0; p.sw32 = 0; p.nq0 = p.nq1 = 0; p.q_bytes = 0; p.fold = 0;
