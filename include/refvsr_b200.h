@@ -96,6 +96,11 @@ typedef struct rv_conv_desc {
 } rv_conv_desc;
 
 int rv_conv2d(const rv_conv_desc* d, void* stream);
+/* Host-only: the launch plan rv_conv2d's tensor-core path would use on a device with `max_smem_optin` bytes of opt-in shared memory
+ * per block and `num_sms` SMs -> out8 = {mode, smem slots, stages per barrier group, stages per tile, MMA-issuing warps, TMEM
+ * accumulators, nb, dynamic smem bytes}.  No CUDA call is made (pointers in `d` are only tested for null / alignment).  Lets the
+ * ring invariants (every issuing warp owns its slots and accumulators) be checked without a GPU. */
+int rv_conv2d_tc_plan(const rv_conv_desc* d, int max_smem_optin, int num_sms, int32_t* out8);
 
 /* ------------------------------------------------------------------------------------------------
  * rv_resblock - fused residual block  out = act_post( x + conv2( act_mid( conv1(x) ) ) ), 3x3 / stride 1 / pad 1,

@@ -20,6 +20,7 @@ int fail(int code, const char* fmt, ...) {
 
 int conv2d_simt(const rv_conv_desc* d, cudaStream_t st);
 int conv2d_tc(const rv_conv_desc* d, cudaStream_t st);
+int conv2d_tc_plan(const rv_conv_desc* d, int max_smem, int num_sms, int* out);
 
 }  // namespace rv
 
@@ -36,4 +37,9 @@ extern "C" int rv_conv2d(const rv_conv_desc* d, void* stream) {
   if (d->impl == RV_CONV_IMPL_TC) return rv::conv2d_tc(d, (cudaStream_t)stream);
   if (d->impl == RV_CONV_IMPL_SIMT) return rv::conv2d_simt(d, (cudaStream_t)stream);
   return rv::fail(RV_E_INVALID, "rv_conv2d: unknown impl %d", d->impl);
+}
+
+extern "C" int rv_conv2d_tc_plan(const rv_conv_desc* d, int max_smem_optin, int num_sms, int32_t* out8) {
+  RV_REQUIRE(d != nullptr && out8 != nullptr && max_smem_optin > 0 && num_sms > 0, "rv_conv2d_tc_plan: bad arguments");
+  return rv::conv2d_tc_plan(d, max_smem_optin, num_sms, out8);
 }

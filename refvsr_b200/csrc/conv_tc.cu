@@ -942,7 +942,9 @@ static int launch_tc(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& 
   return launch_tc_mode<TI, TR, TO, 0>(tm0, tm1, p, grid, smem, st);
 }
 
-int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
+// Everything about a launch that does not need a device: geometry, layout mode, shared-memory ring, accumulators, issuers.
+// (rv_conv2d_tc_plan exposes it so that the ring / issuer invariants are checked on a machine without a GPU.)
+static int plan_tc(const rv_conv_desc* d, TcP& p, size_t& smem_out, int& nblk_out) {
   RV_REQUIRE(d->stride == 1, "rv_conv2d(tc): stride must be 1 (got %d)", d->stride);
   RV_REQUIRE(d->in_dtype == RV_F16 || d->in_dtype == RV_BF16, "rv_conv2d(tc): activations must be f16/bf16");
   RV_REQUIRE(d->c0 % 8 == 0 && (!d->src1 || d->c1 % 8 == 0), "rv_conv2d(tc): channel counts must be multiples of 8");
@@ -951,13 +953,7 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   RV_REQUIRE(d->nb >= 16 && d->nb <= 96 && d->nb % 16 == 0, "rv_conv2d(tc): nb=%d must be a multiple of 16 in [16,96]", d->nb);
   RV_REQUIRE(d->kh >= 1 && d->kh <= 7 && d->kw >= 1 && d->kw <= 7, "rv_conv2d(tc): kernel size up to 7x7");
   RV_REQUIRE(!d->pixel_shuffle || d->cout % 4 == 0, "rv_conv2d: pixel_shuffle needs cout %% 4 == 0");
-  if (g_num_sms == 0) {
-    int dev = 0;
-    RV_CUDA_OK(cudaGetDevice(&dev));
-    RV_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    RV_CUDA_OK(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  }
-  TcP p;
+  RV_REQUIRE(g_num_sms > 0 && g_max_smem > 0, "rv_conv2d(tc): device limits not set");
   p.Ho = d->H + 2 * d->pad - d->kh + 1;
   p.Wo = d->W + 2 * d->pad - d->kw + 1;
   RV_REQUIRE(p.Ho > 0 && p.Wo > 0, "rv_conv2d: empty output");
@@ -1084,6 +1080,26 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   while (cols < (uint32_t)p.nacc * p.acc_stride) cols <<= 1;
   p.tmem_cols = cols;
 
+  smem_out = smem;
+  nblk_out = nblk;
+  return RV_OK;
+}
+
+int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    RV_CUDA_OK(cudaGetDevice(&dev));
+    RV_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    RV_CUDA_OK(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
+  TcP p;
+  size_t smem = 0;
+  int nblk = 1;
+  {
+    const int rc0 = plan_tc(d, p, smem, nblk);
+    if (rc0) return rc0;
+  }
+  const int rdt = d->res ? d->res_dtype : d->out_dtype;
   CUtensorMap tm0, tm1;
   int rc = make_act_tmap(&tm0, d->src0, p.c0, d->W, d->H, p.bw, p.th + d->kh - 1, p.fmt, p.sw32);
   if (rc) return rc;
@@ -1101,6 +1117,22 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   if (d->in_dtype == RV_BF16 && rdt == RV_BF16 && d->out_dtype == RV_BF16) return launch_tc<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(tm0, tm1, p, grid, smem, st);
   if (d->in_dtype == RV_BF16 && rdt == RV_F32 && d->out_dtype == RV_F32) return launch_tc<__nv_bfloat16, float, float>(tm0, tm1, p, grid, smem, st);
   return fail(RV_E_UNSUPPORTED, "rv_conv2d(tc): unsupported dtype combination in=%d res=%d out=%d", d->in_dtype, rdt, d->out_dtype);
+}
+
+// host-only: the launch plan of rv_conv2d (tensor-core path) for given device limits -> out[8] = {mode, slots, grp, S, nmma, nacc,
+// nb, smem bytes}.  mode: 0 boxes per (kx, chunk), 1 single box, 2 32B-swizzled quads, 3 kx-folded.
+int conv2d_tc_plan(const rv_conv_desc* d, int max_smem, int num_sms, int* out) {
+  const int s0 = g_num_sms, s1 = g_max_smem;
+  g_num_sms = num_sms; g_max_smem = max_smem;
+  TcP p;
+  size_t smem = 0;
+  int nblk = 1;
+  const int rc = plan_tc(d, p, smem, nblk);
+  g_num_sms = s0; g_max_smem = s1;
+  if (rc) return rc;
+  out[0] = p.sw32 ? 2 : (p.fold ? 3 : (p.single_box ? 1 : 0));
+  out[1] = p.slots; out[2] = p.grp; out[3] = p.S; out[4] = p.nmma; out[5] = p.nacc; out[6] = p.NB; out[7] = (int)smem;
+  return RV_OK;
 }
 
 }  // namespace rv
