@@ -76,9 +76,10 @@ class Network(nn.Module):
         self.reuse = bool(_cget(config, 'b200_reuse', True))
         # the reuse cache is only valid when consecutive calls slide the window by exactly one frame (what the reference's
         # own eval loop does, data_loader/datasets.py:222-245).  'sync' (default): every non-first call compares the t-1
-        # overlapping LR / Ref frames with the staged copies on the device (one launch, ~20 MB read) and reads the verdict
-        # back before choosing the schedule - a caller that does NOT slide gets a full recompute, i.e. exactly what the
-        # reference would compute for that call.  'async': same check, verdict read at the NEXT call -> RuntimeError
+        # overlapping LR / Ref frames with the staged copies on the device (one launch, ~20 MB read); a caller that does NOT
+        # slide gets a full recompute, i.e. exactly what the reference would compute for that call (one small D2H + host sync per
+        # call; a speculative variant that launches the window behind the check and reads the verdict afterwards was built and
+        # measured in round 2: no gain within run-to-run noise, so the simpler decide-first form stays).  'async': same check, verdict read at the NEXT call -> RuntimeError
         # (no host sync on the hot path).  'off': trust the caller (round-1 behaviour).
         self.reuse_check = _cget(config, 'b200_reuse_check', 'sync')
         if self.reuse_check not in ('sync', 'async', 'off'):
@@ -640,6 +641,11 @@ class Network(nn.Module):
         fresh = (st is None or caller_first or not self.reuse or is_train or st.get('shape') != shape)
         if not fresh and self.reuse_check != 'off':
             fresh = not self._window_slid_by_one(st, lrs, refs, t, h, w, hr, wr)
+        return self._do_window(b, st, fresh, lrs, refs, shape, is_first_frame, is_log, is_train)
+
+    def _do_window(self, b, st, fresh, lrs, refs, shape, is_first_frame, is_log, is_train):
+        t, h, w, hr, wr = shape
+        mid = t // 2
         if fresh:
             st = {'a0': 0, 'pyr': set(), 'fw': set(), 'bw': set(), 'frame': set(), 'staged': set(),
                   'has_prev': bool(st and st.get('has_prev')) and st.get('shape') == shape, 'shape': shape}
@@ -691,18 +697,11 @@ class Network(nn.Module):
         st['has_prev'] = True
         return out, vis
 
-    def _window_slid_by_one(self, st, lrs, refs, t, h, w, hr, wr):
-        """Reuse guard: frames 0..t-2 of this call must be frames 1..t-1 of the previous one, i.e. equal to the staged ring
-        slots a0+1 .. a0+t-1 (bitwise: the slots are fp32 copies of what the caller passed).  Returns False when the
-        cached per-frame products must not be reused for this call."""
+    def _enqueue_overlap_compare(self, st, lrs, refs, t, h, w, hr, wr):
+        """Reuse guard, device side: frames 0..t-2 of this call must be frames 1..t-1 of the previous one, i.e. equal to the
+        staged ring slots a0+1 .. a0+t-1 (bitwise: the slots are fp32 copies of what the caller passed).  Enqueues the comparison;
+        returns the int32 device flag (non-zero = the window did NOT slide by one)."""
         flag = self._buf(f'reuse.flag{self._b}', (1,), torch.int32)
-        if self.reuse_check == 'async' and st.get('check_pending'):
-            st['check_pending'] = False
-            if int(flag.item()):
-                self.reuse_fallbacks += 1
-                raise RuntimeError('refvsr_b200: the previous call did not slide the window by one frame '
-                                   '(is_first_frame=False with different overlapping frames); its output reused stale '
-                                   "per-frame products.  Pass is_first_frame=True for a new clip or set b200_reuse_check='sync'")
         a1 = st['a0'] + 1
         lr32 = lrs if (lrs.dtype == torch.float32 and lrs.is_contiguous()) else lrs.float().contiguous()
         rf32 = refs if (refs.dtype == torch.float32 and refs.is_contiguous()) else refs.float().contiguous()
@@ -718,6 +717,19 @@ class Network(nn.Module):
                 flag2 = self._buf(f'reuse.flag{self._b}.{i}', (1,), torch.int32)
                 self.ops.frames_differ(chunk, flag2)
                 flag.bitwise_or_(flag2)
+        return flag
+
+    def _window_slid_by_one(self, st, lrs, refs, t, h, w, hr, wr):
+        """Reuse guard, host side.  Returns False when the cached per-frame products must not be reused for this call."""
+        flag = self._buf(f'reuse.flag{self._b}', (1,), torch.int32)
+        if self.reuse_check == 'async' and st.get('check_pending'):
+            st['check_pending'] = False
+            if int(flag.item()):
+                self.reuse_fallbacks += 1
+                raise RuntimeError('refvsr_b200: the previous call did not slide the window by one frame '
+                                   '(is_first_frame=False with different overlapping frames); its output reused stale '
+                                   "per-frame products.  Pass is_first_frame=True for a new clip or set b200_reuse_check='sync'")
+        flag = self._enqueue_overlap_compare(st, lrs, refs, t, h, w, hr, wr)
         if self.reuse_check == 'async':
             st['check_pending'] = True
             return True

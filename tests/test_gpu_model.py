@@ -183,3 +183,21 @@ def test_full_size_properties():
         fresh = SRNet(cfg).eval().cuda()
         wl, wr = lrs[:7].unsqueeze(0).cuda() if lrs.shape[0] >= 7 else lrs[[0] * 7].unsqueeze(0).cuda(), refs[[0] * 7].unsqueeze(0).cuda()
         fresh(wl, wr, False, False, False)      # no propagated state yet: the reference fails here too
+
+
+def test_reuse_guard_under_cuda_graphs_non_sliding_caller():
+    """With CUDA graphs and reuse on, a caller that does NOT slide by one frame (is_first_frame=False) must still get exactly what a
+    cache-free, graph-free engine computes for the same calls: the overlap check turns such a call into a full recompute."""
+    from refvsr_b200.synth import make_clip, sliding_windows
+    name = 'small_t7_24x32'
+    spec, cfg, net, _, _, _ = build_case(name, 'cuda', b200_precision='bf16')
+    spec, cfg, ref, _, _, _ = build_case(name, 'cuda', b200_precision='bf16', b200_reuse=False, b200_cuda_graphs=False)
+    lrs, refs = make_clip(16, spec['h'], spec['w'], 1, seed=3)
+    wins = list(sliding_windows(lrs, refs, spec['T']))
+    order = list(range(0, 9)) + [11, 12, 13, 5, 6, 7, 8, 9]       # slides (graphs get captured), a jump forward, slides, a jump back
+    for n, k in enumerate(order):
+        _, wl, wr, _ = wins[k]
+        a = net(wl.cuda(), wr.cuda(), n == 0, False, False)['result']
+        b = ref(wl.cuda(), wr.cuda(), n == 0, False, False)['result']
+        assert torch.equal(a, b), f'call {n} (window {k}): {(a - b).abs().max().item():.3e}'
+    assert net.Network.reuse_fallbacks == 2 and len(net.Network._graphs) > 0
