@@ -123,6 +123,22 @@ def ncu_traffic():
     return None
 
 
+def attach_ncu_traffic(entries):
+    """per-launch DRAM traffic (dram__bytes_read + write) of the same kernels from the committed `ncu --set full` captures
+    (profiles/r02_ncu_kernels.json, written by tools/summarize_r02.py); None where no capture exists"""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_ncu_kernels.json')) as f:
+            ncu = json.load(f)
+    except Exception:
+        ncu = {}
+    key = {'warp_up': 'warp_vec', 'warp3': 'warp3', 'gather_aa1': 'gather_blocks', 'aligned_sample': 'aligned_sample2',
+           'reconstruct': 'reconstruct4', 'match_argmax': 'match_tc', 'conv3x3_lr_chain': 'conv_chain'}
+    for k, v in entries.items():
+        cap = ncu.get(key.get(k, ''), None)
+        v['traffic'] = (cap['traffic'] / (60.0 if k == 'conv3x3_lr_chain' else 1.0)) if cap else None
+    return entries
+
+
 def host_threads():
     """threads for the CPU legs: all cores up to 16 - beyond that the oracle's many small ATen ops lose to
     oversubscription (measured on the 128-core GPU host: 128 threads were >10x slower than 8)."""
@@ -679,7 +695,7 @@ def run_ours(args):
             'clocks': clocks, 'clocks_e2e': clocks_e2e,
             'roofline': dict(roof['conv3x3_lr'], kernel='conv_tc_kernel 3x3 C->C @270x480 (+ReLU+residual)',
                              peak_source=peaks['source'], traffic=ncu_traffic()),
-            'roofline_other': {k: v for k, v in roof.items() if k != 'conv3x3_lr'},
+            'roofline_other': attach_ncu_traffic({k: v for k, v in roof.items() if k != 'conv3x3_lr'}),
         }
         if sustained is not None:
             line['sustained'] = sustained
