@@ -730,13 +730,13 @@ def run_reference(args):
     arm (full 270x480 windows - no scaling).  A step = one steady-state window through the unmodified reference's public
     API (SRNet.forward); the propagated state is primed instead of computed by a first window (which would cost 2x a
     steady window and is not what the metric counts).  Bounded: windows are minutes each, so at most
-    REFVSR_REF_BUDGET_S (default 200 s) of them are timed, at least one; `steps` reports how many."""
+    REFVSR_REF_BUDGET_S (default 110 s) of them are timed, at least one; `steps` reports how many."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = host_threads()
     wl = WORKLOADS[args.workload]
-    budget_s = float(os.environ.get('REFVSR_REF_BUDGET_S', '200'))
+    budget_s = float(os.environ.get('REFVSR_REF_BUDGET_S', '110'))
     kind, times = cpu_steady_windows(args.workload, H, W, budget_s=budget_s, max_windows=max(1, args.steps), cores=cores)
     done, t_timed = len(times), sum(times)
     fps = done / t_timed
