@@ -96,6 +96,13 @@ typedef struct rv_conv_desc {
 } rv_conv_desc;
 
 int rv_conv2d(const rv_conv_desc* d, void* stream);
+/* Upper bound of the persistent grid of the following rv_conv2d (tensor-core) launches made by this process; 0 restores one CTA
+ * per SM.  Returns the previous value.  The engine's own scheduling knob, no counterpart in the reference: the forward-branch
+ * step of a window (RefVSR.py:248-277) is independent of its backward branch (RefVSR.py:211-238), so network.py enqueues the two on
+ * different streams with half the SMs each - two capped launches overlap each other's prologue / first-box latency / last-tile tail,
+ * which a single dependent chain of launches exposes once per layer (profiles/r02_trunk_knockout.md). */
+int rv_set_conv_cta_cap(int cap);
+
 /* Host-only: the launch plan rv_conv2d's tensor-core path would use on a device with `max_smem_optin` bytes of opt-in shared memory
  * per block and `num_sms` SMs -> out8 = {mode, smem slots, stages per barrier group, stages per tile, MMA-issuing warps, TMEM
  * accumulators, nb, dynamic smem bytes}.  No CUDA call is made (pointers in `d` are only tested for null / alignment).  Lets the

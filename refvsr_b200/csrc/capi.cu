@@ -21,6 +21,7 @@ int fail(int code, const char* fmt, ...) {
 int conv2d_simt(const rv_conv_desc* d, cudaStream_t st);
 int conv2d_tc(const rv_conv_desc* d, cudaStream_t st);
 int conv2d_tc_plan(const rv_conv_desc* d, int max_smem, int num_sms, int* out);
+int set_conv_cta_cap(int cap);
 
 }  // namespace rv
 
@@ -38,6 +39,8 @@ extern "C" int rv_conv2d(const rv_conv_desc* d, void* stream) {
   if (d->impl == RV_CONV_IMPL_SIMT) return rv::conv2d_simt(d, (cudaStream_t)stream);
   return rv::fail(RV_E_INVALID, "rv_conv2d: unknown impl %d", d->impl);
 }
+
+extern "C" int rv_set_conv_cta_cap(int cap) { return rv::set_conv_cta_cap(cap); }
 
 extern "C" int rv_conv2d_tc_plan(const rv_conv_desc* d, int max_smem_optin, int num_sms, int32_t* out8) {
   RV_REQUIRE(d != nullptr && out8 != nullptr && max_smem_optin > 0 && num_sms > 0, "rv_conv2d_tc_plan: bad arguments");

@@ -905,6 +905,8 @@ static int make_act_tmap(CUtensorMap* m, const void* ptr, int C, int W, int H, i
 
 static int g_num_sms = 0;
 static int g_max_smem = 0;
+static int g_cta_cap = 0;          // rv_set_conv_cta_cap: upper bound of the persistent grid (0 = one CTA per SM)
+int set_conv_cta_cap(int cap) { const int old = g_cta_cap; g_cta_cap = cap > 0 ? cap : 0; return old; }
 
 template <typename TI, typename TR, typename TO, int MODE, bool PS = false>
 static int launch_tc_mode(const CUtensorMap& tm0, const CUtensorMap& tm1, const TcP& p, dim3 grid, size_t smem,
@@ -978,7 +980,7 @@ static int plan_tc(const rv_conv_desc* d, TcP& p, size_t& smem_out, int& nblk_ou
                          (!d->res || d->res_cs == d->cout) && (!d->gate || d->gate_cs == d->cout);
   p.vlast = (d->cout % p.NB == 0) ? 2 : 1;
   p.fast = fast_ok && p.vec_ok && ps_ok && (d->cout % p.NB == 0 || ragged_ok) && d->out_dtype != RV_F32 && rdt != RV_F32 &&
-           d->out_dtype == d->in_dtype && rdt == d->in_dtype && (p.dbg & 31) == 0;   // knock-out bits 32/64/128 are fast-path experiments
+           d->out_dtype == d->in_dtype && rdt == d->in_dtype && (p.dbg & 22) == 0;   // knock-out bits 1 / 8 / 32 / 64 / 128 also work on the fast path, 2 / 4 / 16 need the generic one
   // mode 1 (single box per tile and chunk) when the whole weight set stays resident next to >= 2 boxes
   p.single_box = 0; p.sw32 = 0; p.nq0 = p.nq1 = 0; p.q_bytes = 0; p.fold = 0;
   if (d->layout == 1 || d->layout == 3) {
@@ -1068,7 +1070,11 @@ static int plan_tc(const rv_conv_desc* d, TcP& p, size_t& smem_out, int& nblk_ou
   // (round 2: 48 -> 192 pixel-shuffle conv at 1080x1920, 4 slots / 3 issuers, dead-lock in ~1 of 20 launches;
   // profiles/r02_8k.md).  With tiles-in-flight and accumulators both multiples of the issuer count, consecutive uses of a slot /
   // accumulator always belong to the same issuer and the parity wait is exact.
+#ifdef RV_CONV_EXPERIMENTS
+  const int nmma_env = getenv("REFVSR_NMMA") ? atoi(getenv("REFVSR_NMMA")) : 0;          // (re-read per launch: tools/trunk_bench.py)
+#else
   static const int nmma_env = getenv("REFVSR_NMMA") ? atoi(getenv("REFVSR_NMMA")) : 0;
+#endif
   {
     const int unit = (p.grp == p.S) ? 1 : p.S;                 // smem slots (barrier pairs) per tile
     int tif = p.slots / unit;                                  // whole tiles in flight
@@ -1111,6 +1117,7 @@ int conv2d_tc(const rv_conv_desc* d, cudaStream_t st) {
   }
   const int ntiles = p.tiles_x * p.tiles_y;
   int gx = std::min(ntiles, std::max(1, g_num_sms / nblk));
+  if (g_cta_cap > 0) gx = std::min(gx, std::max(1, g_cta_cap / nblk));     // two capped launches on different streams share the SMs
   dim3 grid(gx, nblk);
   if (d->in_dtype == RV_F16 && rdt == RV_F16 && d->out_dtype == RV_F16) return launch_tc<__half, __half, __half>(tm0, tm1, p, grid, smem, st);
   if (d->in_dtype == RV_F16 && rdt == RV_F32 && d->out_dtype == RV_F32) return launch_tc<__half, float, float>(tm0, tm1, p, grid, smem, st);

@@ -3,10 +3,18 @@
 // Every kernel is NHWC with 16-byte vector accesses where the channel count allows it.
 // Arithmetic follows SURVEY.md appendix A (verified against torch 2.11 by oracle/refvsr_oracle.py).
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
 namespace rv {
+
+#ifndef RV_W3_TILE_DEFAULT
+#define RV_W3_TILE_DEFAULT 0     // 8 x 16 pixels: 32.3 us vs 35.0 (4 x 16) / 38.1 (2 x 16): the flow-tile prologue is exposed per CTA
+#endif
+#ifndef RV_AS_TILE_DEFAULT
+#define RV_AS_TILE_DEFAULT 1     // 4 x 16 cells: measured 25.4 us vs 28.2 us (8 x 16) at 270x480x48 bf16, profiles/r02_pointwise_tiles.md
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // small vector helpers: V elements of T moved as one 16/8/4-byte access
@@ -38,6 +46,64 @@ __device__ __forceinline__ void stv(T* p, const Vec<T, V>& r) {
 #pragma unroll
     for (int i = 0; i < V; ++i) p[i] = r.v[i];
   }
+}
+
+// 16-byte vector number i of a map (i = pixel * vectors-per-pixel + vector, 32-bit): one IMAD.WIDE per address
+template <typename T, int V>
+__device__ __forceinline__ Vec<T, V> ldvi(const T* base, int i) {
+  static_assert(sizeof(T) * V == 16, "16-byte vectors");
+  Vec<T, V> r;
+  *reinterpret_cast<uint4*>(&r) = __ldg(reinterpret_cast<const uint4*>(base) + (unsigned)i);
+  return r;
+}
+template <typename T, int V>
+__device__ __forceinline__ void stvi(T* base, int i, const Vec<T, V>& r) {
+  static_assert(sizeof(T) * V == 16, "16-byte vectors");
+  reinterpret_cast<uint4*>(base)[(unsigned)i] = *reinterpret_cast<const uint4*>(&r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4-tap blend of one channel vector: r = a * w.x + b * w.y + c * w.z + d * w.w in fp32, evaluated for every element as
+// fma(d, w.w, fma(c, w.z, fma(b, w.y, a * w.x))).  The gather kernels are issue-bound as much as HBM-bound (ncu: ~65 % issue
+// utilisation), so the arithmetic runs on packed pairs (sm_100 FFMA2: one issue slot per two lanes' worth of FMAs) and the
+// 16-bit <-> fp32 conversions are done on packed words.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float2 unpack2(const T* p);
+template <>
+__device__ __forceinline__ float2 unpack2<float>(const float* p) { return make_float2(p[0], p[1]); }
+template <>
+__device__ __forceinline__ float2 unpack2<__half>(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+template <>
+__device__ __forceinline__ float2 unpack2<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+template <typename T>
+__device__ __forceinline__ void pack2(T* p, float2 v);
+template <>
+__device__ __forceinline__ void pack2<float>(float* p, float2 v) { p[0] = v.x; p[1] = v.y; }
+template <>
+__device__ __forceinline__ void pack2<__half>(__half* p, float2 v) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v.x, v.y); }
+template <>
+__device__ __forceinline__ void pack2<__nv_bfloat16>(__nv_bfloat16* p, float2 v) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
+}
+
+template <typename T, int V>
+__device__ __forceinline__ Vec<T, V> blend4(const Vec<T, V>& a, const Vec<T, V>& b, const Vec<T, V>& c, const Vec<T, V>& d, float4 w) {
+  static_assert(V % 2 == 0, "blend4 works on pairs");
+  const float2 wx = make_float2(w.x, w.x), wy = make_float2(w.y, w.y), wz = make_float2(w.z, w.z), ww = make_float2(w.w, w.w);
+  Vec<T, V> r;
+#pragma unroll
+  for (int k = 0; k < V; k += 2) {
+    float2 acc = __fmul2_rn(unpack2<T>(&a.v[k]), wx);
+    acc = __ffma2_rn(unpack2<T>(&b.v[k]), wy, acc);
+    acc = __ffma2_rn(unpack2<T>(&c.v[k]), wz, acc);
+    acc = __ffma2_rn(unpack2<T>(&d.v[k]), ww, acc);
+    pack2<T>(&r.v[k], acc);
+  }
+  return r;
 }
 
 // torch.linspace(-1, 1, n)[i]  (symmetric evaluation, aten RangeFactories)
@@ -360,13 +426,8 @@ __global__ void __launch_bounds__(256) warp_vec_kernel(const T* __restrict__ src
     t3[n] = ldv<T, V>(base + (size_t)o.w * C + n * V);
   }
 #pragma unroll
-  for (int n = 0; n < NV; ++n) {
-    Vec<T, V> r;
-#pragma unroll
-    for (int k = 0; k < V; ++k)
-      r.v[k] = from_f<T>(to_f(t0[n].v[k]) * wq.x + to_f(t1[n].v[k]) * wq.y + to_f(t2[n].v[k]) * wq.z + to_f(t3[n].v[k]) * wq.w);
-    stv<T, V>(out + (size_t)(p0 + pl) * C + (size_t)vc * (V * NV) + n * V, r);
-  }
+  for (int n = 0; n < NV; ++n)
+    stv<T, V>(out + (size_t)(p0 + pl) * C + (size_t)vc * (V * NV) + n * V, blend4<T, V>(t0[n], t1[n], t2[n], t3[n], wq));
 }
 
 
@@ -380,8 +441,6 @@ __global__ void __launch_bounds__(256) warp_vec_kernel(const T* __restrict__ src
 // the corner rows shared by vertically adjacent output pixels are fetched from L2 once per CTA (L1 hits), not once per row.
 // Same arithmetic as warp_kernel / warp_vec_kernel (bit-identical results).
 // ---------------------------------------------------------------------------------------------
-constexpr int W3_TH = 8, W3_TW = 16;
-
 __device__ __forceinline__ void warp_corner(float X, float Y, float fx, float fy, int Wo, int Ho, int Wi, int Hi, int Xi, int Yi,
                                             float4& wq, int4& off) {
   float gx = linspace_m1_1(Xi, Wo) + fx / (((float)Wi - 1.0f) / 2.0f);   // models/utils.py:36-43
@@ -404,7 +463,7 @@ __device__ __forceinline__ void warp_corner(float X, float Y, float fx, float fy
   (void)X; (void)Y;
 }
 
-template <typename T>
+template <typename T, int CV, int W3_TH, int W3_TW>      // CV = C / V (16-byte vectors per pixel) when known at compile time, 0 = run-time
 __global__ void __launch_bounds__(256) warp3_kernel(const T* __restrict__ feat, const T* __restrict__ featUP,
                                                     const float* __restrict__ conf, const float* __restrict__ flow, int h, int w,
                                                     int C, T* __restrict__ o_feat, T* __restrict__ o_featUP,
@@ -458,7 +517,7 @@ __global__ void __launch_bounds__(256) warp3_kernel(const T* __restrict__ feat, 
   }
   __syncthreads();
   // ---- phase 2: gathers.  item = (pixel, vector); the 2x feature first (largest), then the LR feature, then conf.
-  const int cv = C / V;
+  const int cv = CV > 0 ? CV : C / V;          // (compile-time constant for the shipped widths: no integer divisions below)
   auto gather = [&](const T* __restrict__ src, T* __restrict__ dst, int pl0, int npl, int tw, int Y0, int X0, int Hh, int Ww) {
     // two (pixel, vector) items per thread and iteration: all eight 16-byte loads are issued before the first use
     const int nit = npl * cv;
@@ -470,29 +529,22 @@ __global__ void __launch_bounds__(256) warp3_kernel(const T* __restrict__ feat, 
       const bool oka = Ya < Hh && Xa < Ww, okb = itb < nit && Yb < Hh && Xb < Ww;
       const float4 wa = s_w[pl0 + pla], wb = s_w[pl0 + plb];
       const int4 oa = s_o[pl0 + pla], ob = s_o[pl0 + plb];            // (offsets of out-of-image pixels are 0: safe to read)
-      const T* ba = src + (size_t)vca * V;
-      const T* bb = src + (size_t)vcb * V;
-      const Vec<T, V> a0 = ldv<T, V>(ba + (size_t)oa.x * C), a1 = ldv<T, V>(ba + (size_t)oa.y * C),
-                      a2 = ldv<T, V>(ba + (size_t)oa.z * C), a3 = ldv<T, V>(ba + (size_t)oa.w * C);
-      const Vec<T, V> b0 = ldv<T, V>(bb + (size_t)ob.x * C), b1 = ldv<T, V>(bb + (size_t)ob.y * C),
-                      b2 = ldv<T, V>(bb + (size_t)ob.z * C), b3 = ldv<T, V>(bb + (size_t)ob.w * C);
-      Vec<T, V> ra, rb;
-#pragma unroll
-      for (int k = 0; k < V; ++k) {
-        ra.v[k] = from_f<T>(to_f(a0.v[k]) * wa.x + to_f(a1.v[k]) * wa.y + to_f(a2.v[k]) * wa.z + to_f(a3.v[k]) * wa.w);
-        rb.v[k] = from_f<T>(to_f(b0.v[k]) * wb.x + to_f(b1.v[k]) * wb.y + to_f(b2.v[k]) * wb.z + to_f(b3.v[k]) * wb.w);
-      }
-      if (oka) stv<T, V>(dst + ((size_t)Ya * Ww + Xa) * C + (size_t)vca * V, ra);
-      if (okb) stv<T, V>(dst + ((size_t)Yb * Ww + Xb) * C + (size_t)vcb * V, rb);
+      // addresses as 32-bit indices of 16-byte vectors (pixel * cv + vector; the launcher checks that they fit)
+      const Vec<T, V> a0 = ldvi<T, V>(src, oa.x * cv + vca), a1 = ldvi<T, V>(src, oa.y * cv + vca),
+                      a2 = ldvi<T, V>(src, oa.z * cv + vca), a3 = ldvi<T, V>(src, oa.w * cv + vca);
+      const Vec<T, V> b0 = ldvi<T, V>(src, ob.x * cv + vcb), b1 = ldvi<T, V>(src, ob.y * cv + vcb),
+                      b2 = ldvi<T, V>(src, ob.z * cv + vcb), b3 = ldvi<T, V>(src, ob.w * cv + vcb);
+      if (oka) stvi<T, V>(dst, (Ya * Ww + Xa) * cv + vca, blend4<T, V>(a0, a1, a2, a3, wa));
+      if (okb) stvi<T, V>(dst, (Yb * Ww + Xb) * cv + vcb, blend4<T, V>(b0, b1, b2, b3, wb));
     }
   };
   gather(featUP, o_featUP, NLR, NUP, 2 * W3_TW, 2 * ty0, 2 * tx0, H2, W2);
   gather(feat, o_feat, 0, NLR, W3_TW, ty0, tx0, h, w);
-  if (threadIdx.x < NLR) {
-    const int Y = ty0 + threadIdx.x / W3_TW, X = tx0 + threadIdx.x % W3_TW;
+  for (int i = threadIdx.x; i < NLR; i += blockDim.x) {
+    const int Y = ty0 + i / W3_TW, X = tx0 + i % W3_TW;
     if (Y < h && X < w) {
-      const float4 wq = s_w[threadIdx.x];
-      const int4 o = s_o[threadIdx.x];
+      const float4 wq = s_w[i];
+      const int4 o = s_o[i];
       // same accumulation order as warp_kernel<float, 1> (taps nw, ne, sw, se added one by one)
       float acc = 0.f;
       acc += __ldg(conf + o.x) * wq.x;
@@ -575,6 +627,34 @@ __global__ void gather_blocks_kernel(const uint8_t* __restrict__ value, int Hv, 
   else *reinterpret_cast<uint16_t*>(d) = *reinterpret_cast<const uint16_t*>(s);
 }
 
+// 16-byte rows, ks = 1 / 2: one thread = one (cell, 16-byte vector) - the index lookup and its division are done once per
+// cell and the thread then moves the ks * ks pixels of the cell (the per-output-vector version above spends ~190 instructions,
+// six integer divisions among them, on every 16 bytes).  blockIdx.y = cell row.  Pure copies: bit-identical.
+template <int KS, int NVC>
+__global__ void __launch_bounds__(256) gather_cells_kernel(const uint4* __restrict__ value, int Wv, int nv_rt,
+                                                           const int32_t* __restrict__ idx, int wq, uint4* __restrict__ out) {
+  const int nv = NVC > 0 ? NVC : nv_rt;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int cj = j / nv, v = j - cj * nv;
+  if (cj >= wq) return;
+  const int ci = blockIdx.y;
+  const int r = __ldg(idx + ci * wq + cj);
+  const int wvk = Wv / KS;
+  const int ry = r / wvk, rx = r - ry * wvk;
+  const int Wo = KS * wq;
+  const uint4* s = value + ((size_t)(KS * ry) * Wv + KS * rx) * nv + v;
+  uint4* d = out + ((size_t)(KS * ci) * Wo + KS * cj) * nv + v;
+  uint4 t[KS * KS];
+#pragma unroll
+  for (int a = 0; a < KS; ++a)
+#pragma unroll
+    for (int b = 0; b < KS; ++b) t[a * KS + b] = __ldg(s + ((size_t)a * Wv + b) * nv);
+#pragma unroll
+  for (int a = 0; a < KS; ++a)
+#pragma unroll
+    for (int b = 0; b < KS; ++b) d[((size_t)a * Wo + b) * nv] = t[a * KS + b];
+}
+
 // space-to-depth (factor 2): out[(Y,X)][(ry*2+rx)*C + c] = in[(2Y+ry, 2X+rx)][c]; 16-byte vectors
 __global__ void space_to_depth2_kernel(const uint4* __restrict__ src, int H, int W, int cv,
                                        uint4* __restrict__ out) {
@@ -636,65 +716,63 @@ __global__ void aligned_sample_kernel(const T* __restrict__ x, int h, int w, int
 }
 
 
-// ks = 2 (every x4 model): 2-D tiles of 8 x 16 cells = 16 x 32 output pixels.  Phase 1 evaluates the affine sampling position
-// ONCE per output pixel (the per-thread version above recomputes sin / cos / floor / reflect for each of the C/8 channel
-// vectors of a pixel) into shared memory, phase 2 is the same branch-free 4-tap gather as warp3_kernel.  Same arithmetic.
-template <typename T>
+// ks = 2 (every x4 model): 2-D tiles of AS_TH x 16 cells = 2 AS_TH x 32 output pixels.  Phase 1 evaluates the affine sampling
+// positions ONCE per cell - sin / cos once, then the four samples of the cell (the per-thread version above recomputes
+// sin / cos / floor / reflect for each of the C/8 channel vectors of a pixel) - into shared memory, phase 2 is the same
+// branch-free 4-tap gather as warp3_kernel.  Same arithmetic.
+template <typename T, int CV, int AS_TH>
 __global__ void __launch_bounds__(256) aligned_sample2_kernel(const T* __restrict__ x, int h, int w, int C,
                                                               const float* __restrict__ affine, T* __restrict__ out) {
   constexpr int V = 16 / (int)sizeof(T);
-  constexpr int ks = 2, NP = 4 * W3_TH * W3_TW;
+  constexpr int ks = 2, AS_TW = 16, NC = AS_TH * AS_TW, NP = 4 * NC, PW = 2 * AS_TW;
   __shared__ float4 s_w[NP];
   __shared__ int4 s_o[NP];
   const int H = ks * h, W = ks * w, Hp = H + 2, Wp = W + 2;
-  const int tiles_x = (w + W3_TW - 1) / W3_TW;
-  const int Y0 = 2 * (blockIdx.x / tiles_x) * W3_TH, X0 = 2 * (blockIdx.x % tiles_x) * W3_TW;
-  for (int i = threadIdx.x; i < NP; i += blockDim.x) {
-    const int Y = Y0 + i / (2 * W3_TW), X = X0 + i % (2 * W3_TW);
-    float4 wq = make_float4(0.f, 0.f, 0.f, 0.f);
-    int4 off = make_int4(0, 0, 0, 0);
-    if (Y < H && X < W) {
-      const int ci = Y / ks, a = Y % ks, cj = X / ks, b = X % ks;
-      const float* af = affine + ((size_t)ci * w + cj) * 3;
-      float s_x = af[0], s_y = af[1], th = (af[2] - 1.0f) * 1.0472f;
-      float half = (float)((ks - 1) / 2) + 0.5f;
-      float u = ((float)a - half) * s_x, v = ((float)b - half) * s_y;
-      float cs = cosf(th), sn = sinf(th);
-      float rr = u * cs - v * sn, cc = u * sn + v * cs;
-      float pr = rr + half + (float)(1 + ci * ks);
-      float pc = cc + half + (float)(1 + cj * ks);
-      float ltr = floorf(pr), ltc = floorf(pc);
-      float rbr = ltr + 1.f, rbc = ltc + 1.f;
-      const float Hm = (float)(Hp - 1), Wm = (float)(Wp - 1);
-      ltr = fminf(fmaxf(ltr, 0.f), Hm); rbr = fminf(fmaxf(rbr, 0.f), Hm);
-      ltc = fminf(fmaxf(ltc, 0.f), Wm); rbc = fminf(fmaxf(rbc, 0.f), Wm);
-      pr = fminf(fmaxf(pr, 0.f), Hm); pc = fminf(fmaxf(pc, 0.f), Wm);
-      // order (lt, rb, lb, rt) as in aligned_sample_kernel
-      wq = make_float4((1.f + (ltr - pr)) * (1.f + (ltc - pc)), (1.f - (rbr - pr)) * (1.f - (rbc - pc)),
-                       (1.f + (ltr - pr)) * (1.f - (rbc - pc)), (1.f - (rbr - pr)) * (1.f + (ltc - pc)));
-      const int r0 = reflect1((int)ltr - 1, H), r1 = reflect1((int)rbr - 1, H);
-      const int c0 = reflect1((int)ltc - 1, W), c1 = reflect1((int)rbc - 1, W);
-      off = make_int4(r0 * W + c0, r1 * W + c1, r0 * W + c1, r1 * W + c0);
-    }
-    s_w[i] = wq;
-    s_o[i] = off;
+  const int tiles_x = (w + AS_TW - 1) / AS_TW;
+  const int ci0 = (blockIdx.x / tiles_x) * AS_TH, cj0 = (blockIdx.x % tiles_x) * AS_TW;
+  const int Y0 = 2 * ci0, X0 = 2 * cj0;
+  for (int c = threadIdx.x; c < NC; c += blockDim.x) {
+    const int li = c / AS_TW, lj = c % AS_TW;
+    const int ci = ci0 + li, cj = cj0 + lj;
+    if (ci >= h || cj >= w) continue;                       // (entries of cells outside the image are never read)
+    const float* af = affine + ((size_t)ci * w + cj) * 3;
+    const float s_x = af[0], s_y = af[1], th = (af[2] - 1.0f) * 1.0472f;
+    const float half = (float)((ks - 1) / 2) + 0.5f;
+    const float cs = cosf(th), sn = sinf(th);
+    const float Hm = (float)(Hp - 1), Wm = (float)(Wp - 1);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const float u = ((float)a - half) * s_x, v = ((float)b - half) * s_y;
+        const float rr = u * cs - v * sn, cc = u * sn + v * cs;
+        float pr = rr + half + (float)(1 + ci * ks);
+        float pc = cc + half + (float)(1 + cj * ks);
+        float ltr = floorf(pr), ltc = floorf(pc);
+        float rbr = ltr + 1.f, rbc = ltc + 1.f;
+        ltr = fminf(fmaxf(ltr, 0.f), Hm); rbr = fminf(fmaxf(rbr, 0.f), Hm);
+        ltc = fminf(fmaxf(ltc, 0.f), Wm); rbc = fminf(fmaxf(rbc, 0.f), Wm);
+        pr = fminf(fmaxf(pr, 0.f), Hm); pc = fminf(fmaxf(pc, 0.f), Wm);
+        const int r0 = reflect1((int)ltr - 1, H), r1 = reflect1((int)rbr - 1, H);
+        const int c0 = reflect1((int)ltc - 1, W), c1 = reflect1((int)rbc - 1, W);
+        const int e = (2 * li + a) * PW + 2 * lj + b;
+        // order (lt, rb, lb, rt) as in aligned_sample_kernel
+        s_w[e] = make_float4((1.f + (ltr - pr)) * (1.f + (ltc - pc)), (1.f - (rbr - pr)) * (1.f - (rbc - pc)),
+                             (1.f + (ltr - pr)) * (1.f - (rbc - pc)), (1.f - (rbr - pr)) * (1.f + (ltc - pc)));
+        s_o[e] = make_int4(r0 * W + c0, r1 * W + c1, r0 * W + c1, r1 * W + c0);
+      }
   }
   __syncthreads();
-  const int cv = C / V;
+  const int cv = CV > 0 ? CV : C / V;
   for (int it = threadIdx.x; it < NP * cv; it += blockDim.x) {
     const int pl = it / cv, vc = it - pl * cv;
-    const int Y = Y0 + pl / (2 * W3_TW), X = X0 + pl % (2 * W3_TW);
+    const int Y = Y0 + pl / PW, X = X0 + pl % PW;
     if (Y >= H || X >= W) continue;
     const float4 g = s_w[pl];
     const int4 o = s_o[pl];
-    const T* base = x + (size_t)vc * V;
-    const Vec<T, V> t_lt = ldv<T, V>(base + (size_t)o.x * C), t_rb = ldv<T, V>(base + (size_t)o.y * C),
-                    t_lb = ldv<T, V>(base + (size_t)o.z * C), t_rt = ldv<T, V>(base + (size_t)o.w * C);
-    Vec<T, V> r;
-#pragma unroll
-    for (int k = 0; k < V; ++k)
-      r.v[k] = from_f<T>(g.x * to_f(t_lt.v[k]) + g.y * to_f(t_rb.v[k]) + g.z * to_f(t_lb.v[k]) + g.w * to_f(t_rt.v[k]));
-    stv<T, V>(out + ((size_t)Y * W + X) * C + (size_t)vc * V, r);
+    const Vec<T, V> t_lt = ldvi<T, V>(x, o.x * cv + vc), t_rb = ldvi<T, V>(x, o.y * cv + vc),
+                    t_lb = ldvi<T, V>(x, o.z * cv + vc), t_rt = ldvi<T, V>(x, o.w * cv + vc);
+    stvi<T, V>(out, (Y * W + X) * cv + vc, blend4<T, V>(t_lt, t_rb, t_lb, t_rt, g));
   }
 }
 
@@ -1012,14 +1090,32 @@ extern "C" int rv_warp3(const void* feat, const void* featUP, const float* conf,
   RV_REQUIRE(feat && featUP && conf && flow && out_feat && out_featUP && out_conf && h > 0 && w > 0, "rv_warp3: bad arguments");
   RV_REQUIRE(dtype == RV_F16 || dtype == RV_BF16, "rv_warp3: f16 / bf16 features only (use rv_warp for fp32)");
   RV_REQUIRE(C > 0 && C % 8 == 0, "rv_warp3: C=%d must be a multiple of 8", C);
-  const int tiles = ((h + W3_TH - 1) / W3_TH) * ((w + W3_TW - 1) / W3_TW);
-  if (dtype == RV_F16)
-    warp3_kernel<__half><<<tiles, 256, 0, (cudaStream_t)stream>>>((const __half*)feat, (const __half*)featUP, conf, flow, h, w, C,
-                                                                    (__half*)out_feat, (__half*)out_featUP, out_conf);
-  else
-    warp3_kernel<__nv_bfloat16><<<tiles, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)feat, (const __nv_bfloat16*)featUP, conf,
-                                                                           flow, h, w, C, (__nv_bfloat16*)out_feat,
-                                                                           (__nv_bfloat16*)out_featUP, out_conf);
+  RV_REQUIRE((long long)4 * h * w * (C / 8) < (1ll << 31), "rv_warp3: map too large for 32-bit vector indices");
+  // tile shape (REFVSR_W3_TILE: 0 = 8 x 16 LR pixels / 256 threads, 1 = 4 x 16 / 256, 2 = 2 x 16 / 160).  Measured at 270x480x48 bf16:
+  // 32.3 / 35.0 / 38.1 us - every CTA pays the flow-tile load and two barriers before its first gather, so fewer, larger tiles win
+  // here (the opposite of aligned_sample2, whose single wave of 8 x 16 tiles ran its two phases in lock-step on every SM)
+  static const int tile_env = getenv("REFVSR_W3_TILE") ? atoi(getenv("REFVSR_W3_TILE")) : RV_W3_TILE_DEFAULT;
+  auto launch = [&](auto tag, auto cvtag, auto thtag) {
+    using T = decltype(tag);
+    constexpr int TH = decltype(thtag)::value, TW = 16;
+    const int tiles = ((h + TH - 1) / TH) * ((w + TW - 1) / TW);
+    const int threads = TH == 2 ? 160 : 256;
+    warp3_kernel<T, decltype(cvtag)::value, TH, TW><<<tiles, threads, 0, (cudaStream_t)stream>>>(
+        (const T*)feat, (const T*)featUP, conf, flow, h, w, C, (T*)out_feat, (T*)out_featUP, out_conf);
+  };
+  auto by_tile = [&](auto tag, auto cvtag) {
+    if (tile_env == 2) launch(tag, cvtag, std::integral_constant<int, 2>{});
+    else if (tile_env == 1) launch(tag, cvtag, std::integral_constant<int, 4>{});
+    else launch(tag, cvtag, std::integral_constant<int, 8>{});
+  };
+  auto by_cv = [&](auto tag) {           // the reference's widths (48 / 24 channels, config_RefVSR_*.py) + powers of two
+    if (C == 48) by_tile(tag, std::integral_constant<int, 6>{});
+    else if (C == 24) by_tile(tag, std::integral_constant<int, 3>{});
+    else if (C == 64) by_tile(tag, std::integral_constant<int, 8>{});
+    else by_tile(tag, std::integral_constant<int, 0>{});
+  };
+  if (dtype == RV_F16) by_cv(__half{});
+  else by_cv(__nv_bfloat16{});
   RV_LAUNCH_CHECK("warp3");
   return RV_OK;
 }
@@ -1047,7 +1143,19 @@ extern "C" int rv_gather_blocks(const void* value, int Hv, int Wv, int C, int dt
   const uint8_t* v = (const uint8_t*)value;
   uint8_t* o = (uint8_t*)out;
   bool a16 = ((uintptr_t)value % 16 == 0) && ((uintptr_t)out % 16 == 0);
-  if (rowbytes % 16 == 0 && a16)
+  static const bool fast_ok = getenv("REFVSR_NO_FAST_POINTWISE") == nullptr;
+  if (fast_ok && rowbytes % 16 == 0 && a16 && (ks == 1 || ks == 2) && hq <= 65535) {
+    const int nv = rowbytes / 16;
+    const dim3 grid((unsigned)cdiv((long long)wq * nv, 256), (unsigned)hq);
+    const uint4* v4 = (const uint4*)value;
+    uint4* o4 = (uint4*)out;
+    if (ks == 2 && nv == 6) gather_cells_kernel<2, 6><<<grid, 256, 0, st>>>(v4, Wv, nv, idx, wq, o4);
+    else if (ks == 2 && nv == 3) gather_cells_kernel<2, 3><<<grid, 256, 0, st>>>(v4, Wv, nv, idx, wq, o4);
+    else if (ks == 2) gather_cells_kernel<2, 0><<<grid, 256, 0, st>>>(v4, Wv, nv, idx, wq, o4);
+    else if (nv == 6) gather_cells_kernel<1, 6><<<grid, 256, 0, st>>>(v4, Wv, nv, idx, wq, o4);
+    else if (nv == 3) gather_cells_kernel<1, 3><<<grid, 256, 0, st>>>(v4, Wv, nv, idx, wq, o4);
+    else gather_cells_kernel<1, 0><<<grid, 256, 0, st>>>(v4, Wv, nv, idx, wq, o4);
+  } else if (rowbytes % 16 == 0 && a16)
     gather_blocks_kernel<16><<<cdiv(px * (rowbytes / 16), 256), 256, 0, st>>>(v, Hv, Wv, rowbytes, idx, hq, wq, ks, o);
   else if (rowbytes % 4 == 0)
     gather_blocks_kernel<4><<<cdiv(px * (rowbytes / 4), 256), 256, 0, st>>>(v, Hv, Wv, rowbytes, idx, hq, wq, ks, o);
@@ -1064,8 +1172,25 @@ static int aligned_sample_launch(const void* x, int h, int w, int ks, int C, con
   long long px = (long long)ks * h * ks * w;
   bool a16 = ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
   static const bool fast_ok = getenv("REFVSR_NO_FAST_POINTWISE") == nullptr;
-  if (fast_ok && ks == 2 && C % VMAX == 0 && a16)
-    aligned_sample2_kernel<T><<<((h + W3_TH - 1) / W3_TH) * ((w + W3_TW - 1) / W3_TW), 256, 0, st>>>((const T*)x, h, w, C, affine, (T*)out);
+  if (fast_ok && ks == 2 && C % VMAX == 0 && a16 && px * (C / VMAX) < (1ll << 31))       // (32-bit vector indices)
+  {
+    static const int tile_env = getenv("REFVSR_AS_TILE") ? atoi(getenv("REFVSR_AS_TILE")) : RV_AS_TILE_DEFAULT;
+    const int cv = C / VMAX;
+    auto launch = [&](auto cvtag, auto thtag) {
+      constexpr int TH = decltype(thtag)::value;
+      const int tiles = ((h + TH - 1) / TH) * ((w + 15) / 16);
+      aligned_sample2_kernel<T, decltype(cvtag)::value, TH><<<tiles, TH == 2 ? 128 : 256, 0, st>>>((const T*)x, h, w, C, affine, (T*)out);
+    };
+    auto by_tile = [&](auto cvtag) {
+      if (tile_env == 2) launch(cvtag, std::integral_constant<int, 2>{});
+      else if (tile_env == 1) launch(cvtag, std::integral_constant<int, 4>{});
+      else launch(cvtag, std::integral_constant<int, 8>{});
+    };
+    if (cv == 6) by_tile(std::integral_constant<int, 6>{});
+    else if (cv == 3) by_tile(std::integral_constant<int, 3>{});
+    else if (cv == 12) by_tile(std::integral_constant<int, 12>{});
+    else by_tile(std::integral_constant<int, 0>{});
+  }
   else if (C % VMAX == 0 && a16)
     aligned_sample_kernel<T, VMAX><<<cdiv(px * (C / VMAX), 256), 256, 0, st>>>((const T*)x, h, w, ks, C, affine, (T*)out);
   else

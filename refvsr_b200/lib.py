@@ -64,6 +64,7 @@ SIGNATURES = {
     'rv_version': (_I, []),
     'rv_launch_count': (C.c_uint64, []),
     'rv_conv2d': (_I, [C.POINTER(rv_conv_desc), _P]),
+    'rv_set_conv_cta_cap': (_I, [_I]),
     'rv_conv2d_tc_plan': (_I, [C.POINTER(rv_conv_desc), _I, _I, C.POINTER(C.c_int32)]),
     'rv_resblock': (_I, [C.POINTER(rv_resblock_desc), _P]),
     'rv_conv_chain': (_I, [C.POINTER(rv_conv_chain_desc), _P]),
@@ -145,6 +146,10 @@ class CudaOps:
 
     def launch_count(self):
         return int(self.lib.rv_launch_count())
+
+    def set_conv_cta_cap(self, cap):
+        """persistent-grid bound of the following tensor-core conv launches (0 = one CTA per SM); returns the previous value"""
+        return int(self.lib.rv_set_conv_cta_cap(int(cap)))
 
     # -- convolution ------------------------------------------------------------------------------
     def conv2d(self, layer, src0, src1, out, gate=None, res=None, act_pre=ACT_NONE, act_post=ACT_NONE,

@@ -316,9 +316,10 @@ def test_stride2_conv_via_space_to_depth_on_tensor_cores(cuda_ops, oracle_ops):
         close(out, exp, 4e-3, f's2d conv k={k}')
 
 
+@pytest.mark.parametrize('C', [48, 24, 40, 4])          # 6 / 3 vectors per row (compiled widths), 5 (run-time width), 8-byte rows
 @pytest.mark.parametrize('ks', [1, 2])
-def test_gather_blocks(cuda_ops, oracle_ops, ks):
-    hq, wq, C = 14, 22, 48
+def test_gather_blocks(cuda_ops, oracle_ops, ks, C):
+    hq, wq = 14, 45
     Hv, Wv = 9 * ks, 13 * ks
     value = rnd((Hv, Wv, C), 1, torch.float16)
     idx = torch.randint(0, (Hv // ks) * (Wv // ks), (hq * wq,), generator=g(2), dtype=torch.int32)
@@ -328,20 +329,21 @@ def test_gather_blocks(cuda_ops, oracle_ops, ks):
     assert torch.equal(got.cpu(), exp), 'gather is a pure copy: must be bit exact'
 
 
-@pytest.mark.parametrize('prec', ['fp32', 'fp16'])
-def test_aligned_sample(cuda_ops, oracle_ops, prec):
+@pytest.mark.parametrize('C', [48, 40])
+@pytest.mark.parametrize('prec', ['fp32', 'fp16', 'bf16'])
+def test_aligned_sample(cuda_ops, oracle_ops, prec, C):
     dt = DT[prec]
-    h, w, C, ks = 13, 17, 48, 2
+    h, w, ks = 13, 17, 2
     x = rnd((ks * h, ks * w, C), 1, dt)
     aff = (1.0 + rnd((h, w, 3), 2, scale=1.5)).clamp(-3, 3)
     got, exp = both(lambda a, b, o: oracle_ops.aligned_sample(a, b, ks, o), lambda a, b, o: cuda_ops.aligned_sample(a, b, ks, o),
                     (x, aff), (ks * h, ks * w, C), dt)
-    close(got, exp, 2e-4 if dt == torch.float32 else 3e-3, 'aligned_sample')
+    close(got, exp, 2e-4 if dt == torch.float32 else (3e-3 if prec == 'fp16' else 2.5e-2), 'aligned_sample')
     # identity at affine == (1,1,1) (SURVEY 8c known-answer fact)
     one = torch.ones((h, w, 3))
     got, _ = both(lambda a, b, o: oracle_ops.aligned_sample(a, b, ks, o), lambda a, b, o: cuda_ops.aligned_sample(a, b, ks, o),
                   (x, one), (ks * h, ks * w, C), dt)
-    close(got, x, 1e-6 if dt == torch.float32 else 1e-3, 'aligned_sample identity')
+    close(got, x, 1e-6 if dt == torch.float32 else (1e-3 if prec == 'fp16' else 8e-3), 'aligned_sample identity')
 
 
 def test_bicubic_conf_reconstruct(cuda_ops, oracle_ops):
@@ -515,7 +517,7 @@ def test_conv_chain_more_than_64_layers_and_errors(cuda_ops):
 
 
 @pytest.mark.parametrize('prec', ['fp16', 'bf16'])
-@pytest.mark.parametrize('h,w,C', [(24, 40, 48), (37, 53, 24), (270, 480, 48)])
+@pytest.mark.parametrize('h,w,C', [(24, 40, 48), (37, 53, 24), (19, 23, 64), (19, 23, 40), (270, 480, 48)])
 def test_warp3_equals_three_warps(cuda_ops, prec, h, w, C):
     """rv_warp3 (one launch, one flow read, 2-D tiles) against the three rv_warp launches it replaces: same formulas; the LR
     feature and confidence are bit-identical, the 2x feature may differ in the last bit where the compiler contracts the

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 exp = os.path.join(ROOT, 'refvsr_b200', 'librefvsr_b200_exp.so')
 if not os.path.isfile(exp):
-    src = [os.path.join(ROOT, 'refvsr_b200', 'csrc', f) for f in ('capi.cu', 'pointwise.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_rb.cu', 'match.cu')]
+    src = [os.path.join(ROOT, 'refvsr_b200', 'csrc', f) for f in ('capi.cu', 'pointwise.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_rb.cu', 'conv_chain.cu', 'match.cu')]
     subprocess.run(['/usr/local/cuda/bin/nvcc', '-DRV_CONV_EXPERIMENTS', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17',
                     '-Xcompiler', '-fPIC', '-shared', '-o', exp] + src, check=True)
 import torch
