@@ -196,6 +196,21 @@ def kernel_rooflines(net, peaks):
     out['conv3x3_lr'] = dict(bound='tensor', achieved=flops / tconv / 1e12, peak=peaks['tensor_burst'], unit='TFLOP/s',
                              frac=flops / tconv / 1e12 / peaks['tensor_burst'], seconds=tconv,
                              algorithmic_flops=flops, bytes_min=3.0 * C * H * W * e)
+    # the same conv the way the window runs it: 60 dependent launches (30 residual blocks) on ping-pong maps that stay in L2
+    pa, pt, pb = xs[0].clone(), torch.empty_like(xs[0]), torch.empty_like(xs[0])
+
+    def trunk(_):
+        x, y = pa, pb
+        for _i in range(30):
+            ops.conv2d(layer, x, None, pt, act_pre=ACT_RELU)
+            ops.conv2d(layer, pt, None, y, res=x)
+            x, y = y, x
+    ttr = timeit(trunk, iters=2, warm=1) / 60
+    out['conv3x3_lr_trunk'] = dict(bound='tensor', achieved=flops / ttr / 1e12, peak=peaks['tensor_burst'], unit='TFLOP/s',
+                                   frac=flops / ttr / 1e12 / peaks['tensor_burst'], seconds=ttr, algorithmic_flops=flops,
+                                   note='per conv of a 60-launch dependent chain on L2-resident maps (the propagation trunk); '
+                                        '~6.0 us of it is launch / prologue / hand-off skeleton, profiles/r02_trunk_knockout.md')
+    del pa, pt, pb
     # fused residual block (rv_resblock): conv3x3 -> ReLU -> conv3x3 -> + x in one launch
     if net.Network.fuse_resblocks and dt != torch.float32:
         rb = packing.pack_resblock('bench.rbf', w, torch.zeros(C), w, torch.zeros(C), C, dt, dev)

@@ -57,6 +57,7 @@ struct TcP {
   int nacc;                               // accumulator buffers in TMEM (3 or 6)
   int fold;                               // mode 3: the 3 kx taps folded into N = 3 * NB (see conv_tc_kernel MODE 3)
   int fast;                               // streamlined epilogue (all-16-bit, vector stores, full 16-channel chunks)
+  int colsplit;                           // fast epilogue, NB = 48: the three groups share a tile, one 16-column chunk each (1 every tile, 2 the CTA's last)
   int vlast;                              // 16-byte vectors of the LAST 16-column chunk that exist in memory (2, or 1 when cout = NB - 8)
   int nmma;                               // MMA-issuing warps in use (1..MAX_MMA), tiles dealt round-robin
   int grp;                                // consecutive stages that share one full/empty barrier pair (1 or S)
@@ -246,19 +247,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   RV_MARK(0);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < p.slots; ++i) {
+  // barrier init spread over the threads of warp 0 (one slot / accumulator each) instead of ~25 serial inits by thread 0: the
+  // prologue is on every launch's critical path (profiles/r02_trunk_knockout.md)
+  if (threadIdx.x < 32) {
+    const int i = threadIdx.x;
+    if (i < p.slots) {
       tc::mbar_init(&bar_full[i], 1);
       tc::mbar_init(&bar_empty[i], 1);
     }
-    tc::mbar_init(&bar_w, 1);
-    for (int i = 0; i < MAX_ACC; ++i) {
+    if (i < MAX_ACC) {
       tc::mbar_init(&bar_tfull[i], 1);
-      tc::mbar_init(&bar_tempty[i], 4);
+      tc::mbar_init(&bar_tempty[i], p.colsplit == 1 ? 4 * NACC : 4);      // one arrival per epilogue warp that drains the accumulator
+    }
+    if (i == 31) {
+      tc::mbar_init(&bar_w, 1);
+      tc::prefetch_tmap(&tm0);
+      if (p.nch1) tc::prefetch_tmap(&tm1);
     }
     tc::fence_barrier_init();
-    tc::prefetch_tmap(&tm0);
-    if (p.nch1) tc::prefetch_tmap(&tm1);
   }
   if (warp == 1 + MAX_MMA) tc::tmem_alloc(&tmem_base_s, p.tmem_cols);
   for (int i = threadIdx.x; i < p.NB; i += blockDim.x) {
@@ -586,11 +592,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         const int nch = p.NB >> 4;
         const int act_pre = (pre_slope == 1.f) ? 0 : (pre_slope == 0.f ? 1 : 2);
         const int act_post = (post_slope == 1.f) ? 0 : (post_slope == 0.f ? 1 : 2);
+        // p.colsplit (NB = 48): 1 = every tile of the CTA, 2 = only its LAST tile is drained by all three groups together, one
+        // 16-column chunk each (second block below); the per-tile loop here then stops before that tile
+        const int ntl = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // local tiles of this CTA (>= 1)
+        const int last_tile = (int)blockIdx.x + (ntl - 1) * (int)gridDim.x;
+        const int split = PS ? 0 : p.colsplit;
+        const int tile_end = (split == 1) ? 0 : (split == 2 ? last_tile : ntiles);
         // residual vectors are fetched one tile ahead (see the MODE 3 branch above)
         const int nbase = nblk * p.NB;
         auto tile_pixel = [&](const TileIter& it, bool& valid) -> size_t {
           const int oy = it.ty * p.th + ty, ox = it.tx * p.tw + tx;
-          valid = (it.tile < ntiles) && (oy < p.Ho) && (ox < p.Wo);
+          valid = (it.tile < tile_end) && (oy < p.Ho) && (ox < p.Wo);
           return valid ? (size_t)oy * p.Wo + ox : 0;          // out-of-image lanes read pixel 0, never store
         };
         uint4 rp[3][2], rn[3][2];               // residual vectors of the current / next tile
@@ -614,7 +626,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           bool v0;
           fetch_res(tile_pixel(it, v0), rn);
         }
-        for (; it.tile < ntiles; it.next(p.tiles_x, p.nacc)) {
+        for (; it.tile < tile_end; it.next(p.tiles_x, p.nacc)) {
           const int tile = it.tile; (void)tile;
           const uint32_t acc = it.acc, accph = it.accph;
           bool valid, valid_next;
@@ -739,6 +751,115 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
             }
           }
           RV_TRACE(2 + grp, 3, tile);
+        }
+        if (split != 0) {
+        // ---- column-split tiles (NB = 48, the C -> C convs of the propagation trunks and of RAP) ----
+        // All three groups drain the same tile, group g the 16-column chunk g: a warp handles 32 pixels x 16 channels (one
+        // tcgen05.ld.x16, 32 bytes of residual, 32 bytes of output per thread).  Same values as the per-tile loop above; what
+        // changes is the latency of that tile's epilogue (~1/3): the LAST tile of the CTA no longer keeps one group busy for
+        // ~1.8k cycles while the other two idle (7 tiles per CTA, ~10 us per launch: profiles/r02_trunk_knockout.md).  Splitting
+        // EVERY tile (split == 1) was measured slower (10.3 vs 9.8 us per trunk conv): three times the per-tile fixed work.
+        const int n0 = grp * 16;
+        const int nbase = nblk * p.NB + n0;
+        float bias_r[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 b4 = RV_DBG(p, 32) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(&bias_s[n0 + j]);
+          bias_r[j] = b4.x; bias_r[j + 1] = b4.y; bias_r[j + 2] = b4.z; bias_r[j + 3] = b4.w;
+        }
+        // local tiles 0, 1, 2, ... of this CTA: tile t lives in accumulator t % nacc, phase (t / nacc) & 1
+        int tile = (split == 1) ? (int)blockIdx.x : last_tile;
+        int tyi = tile / p.tiles_x, txi = tile - tyi * p.tiles_x;
+        const int dty = gridDim.x / p.tiles_x, dtx = gridDim.x - dty * p.tiles_x;
+        const uint32_t tl0 = (split == 1) ? 0u : (uint32_t)(ntl - 1);
+        uint32_t acc = tl0 % (uint32_t)p.nacc, accph = (tl0 / (uint32_t)p.nacc) & 1u;
+        auto pixel_of = [&](int tl_, int tyy, int txx, bool& valid) -> size_t {
+          const int oy = tyy * p.th + ty, ox = txx * p.tw + tx;
+          valid = (tl_ < ntiles) && (oy < p.Ho) && (ox < p.Wo);
+          return valid ? (size_t)oy * p.Wo + ox : 0;          // out-of-image lanes read pixel 0, never store
+        };
+        uint4 rp0, rp1, rn0 = make_uint4(0, 0, 0, 0), rn1 = make_uint4(0, 0, 0, 0);     // residual of the current / next tile
+        auto fetch_res = [&](size_t pix, uint4& a, uint4& b) {
+          if (RV_DBG(p, 128)) { a = b = make_uint4(0, 0, 0, 0); }
+          else if (res != nullptr) {
+            const uint4* q4 = reinterpret_cast<const uint4*>(res + pix * p.res_cs + nbase);
+            a = __ldg(q4); b = __ldg(q4 + 1);
+          }
+        };
+        {
+          bool v0;
+          fetch_res(pixel_of(tile, tyi, txi, v0), rn0, rn1);
+        }
+        for (; tile < ntiles; tile += gridDim.x) {
+          bool valid, valid_next;
+          const size_t pix = pixel_of(tile, tyi, txi, valid);
+          rp0 = rn0; rp1 = rn1;
+          txi += dtx; tyi += dty;
+          if (txi >= p.tiles_x) { txi -= p.tiles_x; ++tyi; }
+          fetch_res(pixel_of(tile + (int)gridDim.x, tyi, txi, valid_next), rn0, rn1);
+          RV_TRACE(2 + grp, 0, tile);
+          tc::mbar_wait(&bar_tfull[acc], accph);
+          tc::tc_fence_after();
+          RV_TRACE(2 + grp, 1, tile);
+          uint32_t r[16];
+          tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.acc_stride + (uint32_t)n0, r);
+          tc::tmem_ld_wait();
+          tc::tc_fence_before();
+          __syncwarp();
+          if (split == 1 && lane == 0) tc::mbar_arrive(&bar_tempty[acc]);     // (nobody waits for the last tile's accumulator)
+          if (++acc == (uint32_t)p.nacc) { acc = 0; accph ^= 1u; }
+          RV_TRACE(2 + grp, 2, tile);
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bias_r[j];
+          if (act_pre == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (act_pre == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * pre_slope);
+          }
+          if (gate != nullptr) {
+            const uint4* g4 = reinterpret_cast<const uint4*>(gate + pix * p.gate_cs + nbase);
+            const uint4 ga = __ldg(g4), gb = __ldg(g4 + 1);
+            const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 g2 = unpack2(gw[j], TI());
+              v[2 * j] *= g2.x;
+              v[2 * j + 1] *= g2.y;
+            }
+          }
+          if (res != nullptr) {
+            const uint32_t rw[8] = {rp0.x, rp0.y, rp0.z, rp0.w, rp1.x, rp1.y, rp1.z, rp1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 r2 = unpack2(rw[j], TR());
+              v[2 * j] += r2.x;
+              v[2 * j + 1] += r2.y;
+            }
+          }
+          if (act_post == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (act_post == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * post_slope);
+          }
+          if (p.post_clamp3) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], -3.f), 3.f);
+          }
+          if (valid && !RV_DBG(p, 64)) {
+            uint4 o0, o1;
+            o0.x = pack2(v[0], v[1], TO()); o0.y = pack2(v[2], v[3], TO()); o0.z = pack2(v[4], v[5], TO()); o0.w = pack2(v[6], v[7], TO());
+            o1.x = pack2(v[8], v[9], TO()); o1.y = pack2(v[10], v[11], TO()); o1.z = pack2(v[12], v[13], TO()); o1.w = pack2(v[14], v[15], TO());
+            uint4* o = reinterpret_cast<uint4*>(out + pix * p.out_cs + nbase);
+            o[0] = o0;
+            o[1] = o1;
+          }
+          RV_TRACE(2 + grp, 3, tile);
+        }
         }
         tl = 0x7fffffffu;   // generic loop below is skipped
       }
@@ -982,7 +1103,7 @@ static int plan_tc(const rv_conv_desc* d, TcP& p, size_t& smem_out, int& nblk_ou
   p.fast = fast_ok && p.vec_ok && ps_ok && (d->cout % p.NB == 0 || ragged_ok) && d->out_dtype != RV_F32 && rdt != RV_F32 &&
            d->out_dtype == d->in_dtype && rdt == d->in_dtype && (p.dbg & 22) == 0;   // knock-out bits 1 / 8 / 32 / 64 / 128 also work on the fast path, 2 / 4 / 16 need the generic one
   // mode 1 (single box per tile and chunk) when the whole weight set stays resident next to >= 2 boxes
-  p.single_box = 0; p.sw32 = 0; p.nq0 = p.nq1 = 0; p.q_bytes = 0; p.fold = 0;
+  p.single_box = 0; p.sw32 = 0; p.nq0 = p.nq1 = 0; p.q_bytes = 0; p.fold = 0; p.colsplit = 0;
   if (d->layout == 1 || d->layout == 3) {
     RV_REQUIRE(d->kh == d->kw && (d->kh == 1 || d->kh == 3 || d->kh == 5 || d->kh == 7), "rv_conv2d(tc): layout 1 needs a square 1/3/5/7 kernel");
     p.single_box = 1;
@@ -1028,6 +1149,10 @@ static int plan_tc(const rv_conv_desc* d, TcP& p, size_t& smem_out, int& nblk_ou
     p.w_bytes = (uint32_t)d->kh * p.NB * 128;
   }
   p.tiles_x = (p.Wo + p.tw - 1) / p.tw; p.tiles_y = (p.Ho + p.th - 1) / p.th;
+  {
+    static const int colsplit_mode = getenv("REFVSR_COLSPLIT") ? atoi(getenv("REFVSR_COLSPLIT")) : 0;      // 0 off (default: neither variant paid, see the kernel), 1 all tiles, 2 last tile
+    p.colsplit = (p.fast && !p.fold && !d->pixel_shuffle && p.NB == 16 * NACC && p.vlast == 2) ? colsplit_mode : 0;
+  }
   // shared-memory plan: weights resident when they leave room for >= 3 A slots
   const size_t w_all = (size_t)p.S * p.w_bytes;
   p.grp = 1;

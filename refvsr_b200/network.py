@@ -95,6 +95,21 @@ class Network(nn.Module):
         # profiles/r02_conv_chain.md) -> opt-in.
         self.use_chain = bool(_cget(config, 'b200_conv_chain', False)) and not os.environ.get('REFVSR_NO_CHAIN')
         self.chain_max_ctas = int(_cget(config, 'b200_chain_max_ctas', 0))   # see rv_conv_chain_desc.max_ctas (dist.py sets it)
+        # The forward-branch step of a steady window (RefVSR.py:248-277) needs only the previous call's state and per-frame products
+        # of earlier calls; the products of the entering frame and the backward branch (RefVSR.py:211-238) do not depend on it.
+        # With overlap on, the forward step is enqueued on a second stream (a fork / join inside the window's CUDA graph): the
+        # launches of the two branches fill each other's prologue / first-box latency / last-tile tail (~3.4 of the ~10 us of a
+        # trunk conv, profiles/r02_trunk_knockout.md).  Same kernels, same inputs, same order within each branch: bit-identical
+        # results (tests/test_gpu_model.py::test_branch_overlap_is_exact).  Measured 87.4 -> 89.1 frames/s.  Splitting the SMs
+        # statically between the two streams (rv_set_conv_cta_cap; 8.3 instead of 9.9 us per conv for two SYMMETRIC chains,
+        # profiles/r02_dual_chain.log) loses in the real window - 83.7 frames/s at 74 / 74, 86.3 with only the forward step capped -
+        # because the branches are not symmetric and a cap outlives the overlap; the caps therefore default to 0 (none).
+        self.overlap_branches = bool(_cget(config, 'b200_overlap_branches', True)) and not os.environ.get('REFVSR_NO_OVERLAP')
+        # grid caps: forward step (second stream) / products and the first `overlap_bw_steps` backward steps (main stream); 0 = none
+        self.overlap_cap = int(os.environ.get('REFVSR_OVERLAP_CAP', _cget(config, 'b200_overlap_cap', 0)))
+        self.overlap_main_cap = int(os.environ.get('REFVSR_OVERLAP_MAIN_CAP', _cget(config, 'b200_overlap_main_cap', 0)))
+        self.overlap_bw_steps = int(os.environ.get('REFVSR_OVERLAP_BW_STEPS', _cget(config, 'b200_overlap_bw_steps', 0)))
+        self._side = None
         self._ring_mod = None
         self._shard = None
         self._bufs = {}
@@ -453,34 +468,36 @@ class Network(nn.Module):
         C, dt = self.mid_channels, self.act_dtype
         conf, aligned, aligned_up = fp['conf'], fp['aligned'], fp['aligned_up']
         h, w = conf.shape
+        # scratch maps: one set per branch when the two branches may run concurrently (tag = 'bw.rap0' / 'fw.rap1' ...)
+        sc = (tag.split('.')[0] + '.rap') if self.overlap_branches else 'rap'
         # level 1 (reference alignment already done per frame, see _frame_alignment)
-        cp8 = self._buf('rap.cp8', (h, w, 8), dt)
+        cp8 = self._buf(sc + '.cp8', (h, w, 8), dt)
         self.ops.conf_pair(conf_prop, conf, cp8, up2=False)
-        a0 = self._conv('conf_fusion.0.0', cp8, None, self._buf('rap.a0', (h, w, 16), dt), [(2, 8)], act_pre=ACT_LRELU02)
-        alpha = self._conv('conf_fusion.1.0', a0, None, self._buf('rap.alpha', (h, w, C), dt), [(16, 16)], act_pre=ACT_LRELU02)
-        f0 = self._conv('feat_fusion.0.0', feat_prop, aligned, self._buf('rap.f0', (h, w, C), dt), [(C, C), (C, C)],
+        a0 = self._conv('conf_fusion.0.0', cp8, None, self._buf(sc + '.a0', (h, w, 16), dt), [(2, 8)], act_pre=ACT_LRELU02)
+        alpha = self._conv('conf_fusion.1.0', a0, None, self._buf(sc + '.alpha', (h, w, C), dt), [(16, 16)], act_pre=ACT_LRELU02)
+        f0 = self._conv('feat_fusion.0.0', feat_prop, aligned, self._buf(sc + '.f0', (h, w, C), dt), [(C, C), (C, C)],
                         act_pre=ACT_LRELU02)
-        fused = self._conv('feat_fusion.1.0', f0, None, self._buf('rap.fused', (h, w, C), dt), [(C, C)],
+        fused = self._conv('feat_fusion.1.0', f0, None, self._buf(sc + '.fused', (h, w, C), dt), [(C, C)],
                            act_pre=ACT_LRELU02, gate=alpha, res=feat_prop)
         feat_out = self._buf(tag + '.feat', (h, w, C), dt)
-        self._reslist('feat_decoder', 8, fused, feat_out, 'rap.dec1')
+        self._reslist('feat_decoder', 8, fused, feat_out, sc + '.dec1')
 
         # level 2
-        up = self._conv('upsample1.upsample_conv', feat_out, None, self._buf('rap.up', (2 * h, 2 * w, C), dt), [(C, C)],
+        up = self._conv('upsample1.upsample_conv', feat_out, None, self._buf(sc + '.up', (2 * h, 2 * w, C), dt), [(C, C)],
                         pixel_shuffle=True)
-        fu = self._conv('feat_fusion2_1.0.0', feat_prop_UP, up, self._buf('rap.fu', (2 * h, 2 * w, C), dt),
+        fu = self._conv('feat_fusion2_1.0.0', feat_prop_UP, up, self._buf(sc + '.fu', (2 * h, 2 * w, C), dt),
                         [(C, C), (C, C)], act_pre=ACT_LRELU02)
-        cp8u = self._buf('rap.cp8u', (2 * h, 2 * w, 8), dt)
+        cp8u = self._buf(sc + '.cp8u', (2 * h, 2 * w, 8), dt)
         self.ops.conf_pair(conf_prop, conf, cp8u, up2=True)
-        b0 = self._conv('conf_fusion2.0.0', cp8u, None, self._buf('rap.b0', (2 * h, 2 * w, 16), dt), [(2, 8)], act_pre=ACT_LRELU02)
-        alpha2 = self._conv('conf_fusion2.1.0', b0, None, self._buf('rap.alpha2', (2 * h, 2 * w, C), dt), [(16, 16)],
+        b0 = self._conv('conf_fusion2.0.0', cp8u, None, self._buf(sc + '.b0', (2 * h, 2 * w, 16), dt), [(2, 8)], act_pre=ACT_LRELU02)
+        alpha2 = self._conv('conf_fusion2.1.0', b0, None, self._buf(sc + '.alpha2', (2 * h, 2 * w, C), dt), [(16, 16)],
                             act_pre=ACT_LRELU02)
-        g0 = self._conv('feat_fusion2.0.0', fu, aligned_up, self._buf('rap.g0', (2 * h, 2 * w, C), dt), [(C, C), (C, C)],
+        g0 = self._conv('feat_fusion2.0.0', fu, aligned_up, self._buf(sc + '.g0', (2 * h, 2 * w, C), dt), [(C, C), (C, C)],
                         act_pre=ACT_LRELU02)
-        fused2 = self._conv('feat_fusion2.1.0', g0, None, self._buf('rap.fused2', (2 * h, 2 * w, C), dt), [(C, C)],
+        fused2 = self._conv('feat_fusion2.1.0', g0, None, self._buf(sc + '.fused2', (2 * h, 2 * w, C), dt), [(C, C)],
                             act_pre=ACT_LRELU02, gate=alpha2, res=fu)
         feat_up_out = self._buf(tag + '.featUP', (2 * h, 2 * w, C), dt)
-        self._reslist('feat_decoder2', 4, fused2, feat_up_out, 'rap.dec2')
+        self._reslist('feat_decoder2', 4, fused2, feat_up_out, sc + '.dec2')
         conf_out = self._buf(tag + '.conf', (h, w), torch.float32)
         self.ops.conf_max(conf_prop, conf, conf_out)
         return feat_out, feat_up_out, conf_out
@@ -741,7 +758,7 @@ class Network(nn.Module):
     def _warp3_ok(self):
         return self.act_dtype != torch.float32 and hasattr(self.ops, 'warp3') and not os.environ.get('REFVSR_NO_WARP3')
 
-    def _backward_branch(self, a0, t, h, w, vis=None):
+    def _backward_branch(self, a0, t, h, w, vis=None, after_step=None):
         """backward branch of the window at stream position a0 (RefVSR.py:211-238): window-local, starts from zeros at the
         window's last frame -> (feat_prop_UP, conf_map_prop) buffers at the centre frame"""
         ops = self.ops
@@ -769,6 +786,8 @@ class Network(nn.Module):
             agg = self._prop_resblocks('backward_resblocks', fp['lr8'], feat_prop,
                                        self._buf('bw.agg', (h, w, C), dt), 'bw.rb')
             feat_prop, feat_prop_UP, conf_prop = self._rap(fp, conf_prop, agg, feat_prop_UP, f'bw.rap{i % 2}')
+            if after_step is not None:
+                after_step(t - 1 - i)
         return feat_prop_UP, conf_prop
 
     def _forward_step(self, a, t, h, w, state, flow, quirk, tagi):
@@ -802,40 +821,80 @@ class Network(nn.Module):
         """All kernel launches of one window.  Reads / writes static buffers only (graph-capturable)."""
         C, dt = self.mid_channels, self.act_dtype
         mid = t // 2
-        self._run_products(work, t, h, w, hr, wr)
         vis = {'vis': collections.OrderedDict()} if is_log else None
 
         def lr32(i):
             return self._ring('lr32', a0 + i, t, (3, h, w))
 
-        # ---------------- backward branch (RefVSR.py:211-238) ----------------
-        backward_feat_UP, conf_bw = self._backward_branch(a0, t, h, w, vis)
-        # (the forward branch writes 'fw.*' buffers only, so these stay intact)
-
-        # ---------------- forward branch (RefVSR.py:241-283) ----------------
         if is_first_frame:
             range_start = 0
         prev = {'feat': self._buf(f'prev{b}.feat', (h, w, C), dt), 'featUP': self._buf(f'prev{b}.featUP', (2 * h, 2 * w, C), dt),
                 'conf': self._buf(f'prev{b}.conf', (h, w), torch.float32), 'flow': self._buf(f'prev{b}.flow', (h, w, 2), torch.float32)}
-        state, flow = None, None
-        for i in range(range_start, mid + 1):
-            if i > range_start:
-                flow = self._ring('fw', a0 + i - 1, t, (h, w, 2))
-                state = self._forward_step(a0 + i, t, h, w, state, flow, True, i)
-            elif not is_first_frame:
-                flow = prev['flow']
-                state = self._forward_step(a0 + i, t, h, w, (prev['feat'], prev['featUP'], prev['conf']), flow, False, i)
-            else:
-                state = self._forward_step(a0 + i, t, h, w, None, None, False, i)
-            if is_log and i == mid and flow is not None:
-                vis['vis']['FW_LR_prev_warp'] = self._warp_image(lr32(i - 1), flow)
-            feat_prop, feat_prop_UP, conf_prop = state
-            if (is_train and i == 0) or (not is_train and i == mid):           # RefVSR.py:279-283
-                prev['feat'].copy_(feat_prop)
-                prev['featUP'].copy_(feat_prop_UP)
-                prev['conf'].copy_(conf_prop)
-                if (a0 + i) in st['fw']:
-                    prev['flow'].copy_(self._ring('fw', a0 + i, t, (h, w, 2)))
+
+        def carry_flow(i):
+            if (a0 + i) in st['fw']:
+                prev['flow'].copy_(self._ring('fw', a0 + i, t, (h, w, 2)))
+
+        def forward_branch(copy_flow=True):
+            # ---------------- forward branch (RefVSR.py:241-283) ----------------
+            state, flow = None, None
+            for i in range(range_start, mid + 1):
+                if i > range_start:
+                    flow = self._ring('fw', a0 + i - 1, t, (h, w, 2))
+                    state = self._forward_step(a0 + i, t, h, w, state, flow, True, i)
+                elif not is_first_frame:
+                    flow = prev['flow']
+                    state = self._forward_step(a0 + i, t, h, w, (prev['feat'], prev['featUP'], prev['conf']), flow, False, i)
+                else:
+                    state = self._forward_step(a0 + i, t, h, w, None, None, False, i)
+                if is_log and i == mid and flow is not None:
+                    vis['vis']['FW_LR_prev_warp'] = self._warp_image(lr32(i - 1), flow)
+                feat_prop, feat_prop_UP, conf_prop = state
+                if (is_train and i == 0) or (not is_train and i == mid):           # RefVSR.py:279-283
+                    prev['feat'].copy_(feat_prop)
+                    prev['featUP'].copy_(feat_prop_UP)
+                    prev['conf'].copy_(conf_prop)
+                    if copy_flow:
+                        carry_flow(i)
+            return feat_prop_UP, conf_prop
+
+        # A steady window runs ONE forward step from the carried state: nothing it reads is produced by this call (the flow comes from
+        # the previous call, the alignment products of the centre frame were computed when that frame entered) -> it overlaps the
+        # entering frame's products and the backward branch.  The one exception is the flow carried to the NEXT call (forward_flows[mid],
+        # computed by this call's products): it is copied after the join, which also orders it behind the step's own read of prev.
+        overlap = (self.overlap_branches and self._device.type == 'cuda' and hasattr(self.ops, 'set_conv_cta_cap') and not is_log
+                   and not is_train and not is_first_frame and range_start == mid and ('frame', a0 + mid) not in work
+                   and not self.use_chain)                   # (the chain kernel's tile flags are one shared buffer)
+        if overlap:
+            ops = self.ops
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self._device)
+            side = self._side
+            side.wait_stream(main)                                   # fork (a graph branch under capture)
+            try:
+                ops.set_conv_cta_cap(self.overlap_cap)                # (the cap is read when a launch is enqueued)
+                with torch.cuda.stream(side):
+                    feat_prop_UP, conf_prop = forward_branch(copy_flow=False)
+                ops.set_conv_cta_cap(self.overlap_main_cap)
+                self._run_products(work, t, h, w, hr, wr)
+
+                def after_step(k):
+                    if k + 1 == self.overlap_bw_steps:
+                        ops.set_conv_cta_cap(0)                      # the forward step is over by now: full grids again
+                if self.overlap_bw_steps <= 0:
+                    ops.set_conv_cta_cap(0)
+                backward_feat_UP, conf_bw = self._backward_branch(a0, t, h, w, vis, after_step)
+            finally:
+                ops.set_conv_cta_cap(0)
+                main.wait_stream(side)                               # join
+            carry_flow(mid)
+        else:
+            self._run_products(work, t, h, w, hr, wr)
+            # ---------------- backward branch (RefVSR.py:211-238) ----------------
+            backward_feat_UP, conf_bw = self._backward_branch(a0, t, h, w, vis)
+            # (the forward branch writes 'fw.*' buffers only, so these stay intact)
+            feat_prop_UP, conf_prop = forward_branch()
 
         # ---------------- U (RefVSR.py:286-297) ----------------
         out = self._compute_up(backward_feat_UP, feat_prop_UP, conf_bw, conf_prop, lr32(mid), clamp01=not is_train)

@@ -138,6 +138,29 @@ def test_cuda_graphs_are_exact():
         assert torch.equal(a, b), f'window {k}: graph replay differs from eager'
 
 
+def test_branch_overlap_is_exact():
+    """forward step of a steady window on a second stream + capped conv grids (network.py, rv_set_conv_cta_cap) vs the sequential
+    schedule: bit identical, with CUDA graphs and eagerly, across steady windows, ring wrap-around and forced resets."""
+    from refvsr_b200 import SRNet, get_config
+    from refvsr_b200.modules import seeded_test_weights
+    from refvsr_b200.synth import make_clip, sliding_windows
+    lrs, refs = make_clip(24, 40, 56, 1, seed=9)
+    res = {}
+    for overlap, graphs in ((False, True), (True, True), (True, False)):
+        cfg = get_config('RefVSR_MFID', device='cuda', num_blocks=3, b200_precision='bf16', b200_cuda_graphs=graphs,
+                         b200_overlap_branches=overlap, b200_overlap_cap=70)
+        net = SRNet(cfg).eval()
+        seeded_test_weights(net, seed=9)
+        net = net.cuda()
+        assert net.Network.overlap_branches == overlap
+        res[(overlap, graphs)] = [net(wl.cuda(), wr.cuda(), first, False, False)['result'].cpu()
+                                  for k, wl, wr, first in sliding_windows(lrs, refs, 7)]
+        assert net.Network.ops.set_conv_cta_cap(0) == 0, 'the grid cap must be back to 0 after every window'
+    for key in ((True, True), (True, False)):
+        for k, (a, b) in enumerate(zip(res[key], res[(False, True)])):
+            assert torch.equal(a, b), f'window {k}: overlapped schedule {key} differs from the sequential one'
+
+
 def test_medium_size_against_oracle():
     """96x128 LR, RefVSR_small_MFID with all 24 blocks, 3 windows: CUDA fp32 path vs the CPU oracle."""
     from oracle.refvsr_oracle import OracleRefVSR

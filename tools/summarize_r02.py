@@ -28,6 +28,7 @@ ALGO = {
     'aligned_sample2': ('hbm', 101.1e6, 'K4 AlignedConv2d resampling, tiled kernel (ks = 2)'),
     'reconstruct4': ('hbm', 59.6e6, 'K7 conv_last output + bicubic x4 base + clamp, one thread per LR pixel'),
     'match_tc': ('tensor', 1.209e12, 'K2 matching GEMM + argmax, single pass (default mode)'),
+    'gather_cells': ('hbm', 25.4e6, 'K3 aa1 gather, one thread per (cell, vector) (first gather launch of profile_kernels.py)'),
     'gather_blocks': ('hbm', 25.4e6, 'K3 aa1 gather (first gather_blocks launch of profile_kernels.py)'),
     'aligned_sample': ('hbm', 101.1e6, 'K4 AlignedConv2d resampling of the gathered 2x feature'),
     'reconstruct': ('hbm', 59.6e6, 'K7 conv_last output + bicubic x4 base + clamp'),
