@@ -110,6 +110,7 @@ class Network(nn.Module):
         self.overlap_main_cap = int(os.environ.get('REFVSR_OVERLAP_MAIN_CAP', _cget(config, 'b200_overlap_main_cap', 0)))
         self.overlap_bw_steps = int(os.environ.get('REFVSR_OVERLAP_BW_STEPS', _cget(config, 'b200_overlap_bw_steps', 0)))
         self._side = None
+        self._flow_streams = None
         self._ring_mod = None
         self._shard = None
         self._bufs = {}
@@ -303,22 +304,23 @@ class Network(nn.Module):
             self.ops.avgpool2(lv[l + 1], lv[l])
         return lv
 
-    def _spynet(self, pyr_ref, pyr_supp, out):
-        """flow from ref to supp into `out` (h,w,2) fp32.  pyr_*: outputs of _pyramid."""
+    def _spynet(self, pyr_ref, pyr_supp, out, sp='spy'):
+        """flow from ref to supp into `out` (h,w,2) fp32.  pyr_*: outputs of _pyramid.  sp: scratch-buffer prefix (one set per
+        stream when two flows are computed concurrently, _run_products)."""
         dt = self.act_dtype
         flow = None
         for level in range(6):
             r, s = pyr_ref[level], pyr_supp[level]
             H, W = r.shape[0], r.shape[1]
-            x8 = self._buf('spy.x8', (H, W, 8), dt)
-            flow_up = self._buf('spy.fu', (H, W, 2), torch.float32)
+            x8 = self._buf(sp + '.x8', (H, W, 8), dt)
+            flow_up = self._buf(sp + '.fu', (H, W, 2), torch.float32)
             self.ops.spynet_level_input(r, s, flow, x8, flow_up)
             pre = f'FlowNet.basic_module.{level}.basic_module'
-            a = self._conv(f'{pre}.0.conv', x8, None, self._buf('spy.a', (H, W, 32), dt), [(8, 8)], act_pre=ACT_RELU)
-            b = self._conv(f'{pre}.1.conv', a, None, self._buf('spy.b', (H, W, 64), dt), [(32, 32)], act_pre=ACT_RELU)
-            c = self._conv(f'{pre}.2.conv', b, None, self._buf('spy.c', (H, W, 32), dt), [(64, 64)], act_pre=ACT_RELU)
-            d = self._conv(f'{pre}.3.conv', c, None, self._buf('spy.d', (H, W, 16), dt), [(32, 32)], act_pre=ACT_RELU)
-            flow = self._buf('spy.fl', (H, W, 2), torch.float32)
+            a = self._conv(f'{pre}.0.conv', x8, None, self._buf(sp + '.a', (H, W, 32), dt), [(8, 8)], act_pre=ACT_RELU)
+            b = self._conv(f'{pre}.1.conv', a, None, self._buf(sp + '.b', (H, W, 64), dt), [(32, 32)], act_pre=ACT_RELU)
+            c = self._conv(f'{pre}.2.conv', b, None, self._buf(sp + '.c', (H, W, 32), dt), [(64, 64)], act_pre=ACT_RELU)
+            d = self._conv(f'{pre}.3.conv', c, None, self._buf(sp + '.d', (H, W, 16), dt), [(32, 32)], act_pre=ACT_RELU)
+            flow = self._buf(sp + '.fl', (H, W, 2), torch.float32)
             self._conv(f'{pre}.4.conv', d, None, flow, [(16, 16)], res=flow_up)   # flow_up + residue (SPyNet.py:95)
         self.ops.flow_resize(flow, out)     # SPyNet.py:129-137; RefVSR.py:184,189 resize is the identity
         return out
@@ -577,22 +579,46 @@ class Network(nn.Module):
         return self._buf(f'ring{self._b}.{kind}.{a % self._rm(t)}', shape, dtype)
 
     def _run_products(self, work, t, h, w, hr, wr):
-        for kind, a in work:
-            lr = self._ring('lr32', a, t, (3, h, w))
-            if kind == 'pyr':
-                self._pyramid(lr, a % self._rm(t))
-            elif kind in ('fw', 'bw'):
-                pa = [self._buf(f'ring{self._b}.pyr{l}.{a % self._rm(t)}', (H, W, 3), torch.float32) for l, (H, W) in enumerate(self._pyr_shapes(h, w))]
-                pb = [self._buf(f'ring{self._b}.pyr{l}.{(a + 1) % self._rm(t)}', (H, W, 3), torch.float32) for l, (H, W) in enumerate(self._pyr_shapes(h, w))]
-                out = self._ring(kind, a, t, (h, w, 2))
-                if kind == 'fw':
-                    self._spynet(pb, pa, out)      # Flow(frame a+1, frame a)
-                else:
-                    self._spynet(pa, pb, out)      # Flow(frame a, frame a+1)
-            elif kind in ('fw0', 'bw0'):
-                self._ring(kind[:2], a, t, (h, w, 2)).zero_()
+        """Pyramids first, then the flows and the per-frame alignment products, which are independent of each other.  With
+        b200_overlap_branches the flows (~60 launches of SPyNet's small convs per steady window: grids of 2 - 75 CTAs) go to two
+        side streams - alternating, each with its own scratch maps - and fill the SMs the matching / alignment kernels of the
+        main stream leave idle; everything is joined before this returns.  Same kernels and inputs: bit-identical."""
+        def flow(kind, a, sp):
+            pa = [self._buf(f'ring{self._b}.pyr{l}.{a % self._rm(t)}', (H, W, 3), torch.float32) for l, (H, W) in enumerate(self._pyr_shapes(h, w))]
+            pb = [self._buf(f'ring{self._b}.pyr{l}.{(a + 1) % self._rm(t)}', (H, W, 3), torch.float32) for l, (H, W) in enumerate(self._pyr_shapes(h, w))]
+            out = self._ring(kind, a, t, (h, w, 2))
+            if kind == 'fw':
+                self._spynet(pb, pa, out, sp)      # Flow(frame a+1, frame a)
             else:
-                self._frame_alignment(lr, self._ring('ref32', a, t, (3, hr, wr)), a % self._rm(t))
+                self._spynet(pa, pb, out, sp)      # Flow(frame a, frame a+1)
+
+        for kind, a in work:
+            if kind == 'pyr':
+                self._pyramid(self._ring('lr32', a, t, (3, h, w)), a % self._rm(t))
+        flows = [(kind, a) for kind, a in work if kind in ('fw', 'bw')]
+        par = self.overlap_branches and self._device.type == 'cuda' and len(flows) > 0 and not self.use_chain
+        used = []
+        if par:
+            main = torch.cuda.current_stream()
+            if self._flow_streams is None:
+                self._flow_streams = [torch.cuda.Stream(device=self._device) for _ in range(2)]
+            for n, (kind, a) in enumerate(flows):
+                st_ = self._flow_streams[n % 2]
+                if st_ not in used:
+                    st_.wait_stream(main)              # fork behind the pyramids
+                    used.append(st_)
+                with torch.cuda.stream(st_):
+                    flow(kind, a, f'spy{n % 2}')
+        else:
+            for kind, a in flows:
+                flow(kind, a, 'spy')
+        for kind, a in work:
+            if kind in ('fw0', 'bw0'):
+                self._ring(kind[:2], a, t, (h, w, 2)).zero_()
+            elif kind == 'frame':
+                self._frame_alignment(self._ring('lr32', a, t, (3, h, w)), self._ring('ref32', a, t, (3, hr, wr)), a % self._rm(t))
+        for st_ in used:
+            torch.cuda.current_stream().wait_stream(st_)                # join
 
     # ------------------------------------------------------------------------------------------
     # forward (RefVSR.py:151-325)
