@@ -131,8 +131,8 @@ def attach_ncu_traffic(entries):
             ncu = json.load(f)
     except Exception:
         ncu = {}
-    key = {'warp_up': 'warp_vec', 'warp3': 'warp3', 'gather_aa1': 'gather_blocks', 'aligned_sample': 'aligned_sample2',
-           'reconstruct': 'reconstruct4', 'match_argmax': 'match_tc', 'conv3x3_lr_chain': 'conv_chain'}
+    key = {'warp_up': 'warp_vec', 'warp3': 'warp3', 'gather_aa1': 'gather_cells', 'aligned_sample': 'aligned_sample2',
+           'reconstruct': 'reconstruct4', 'match_argmax': 'match_tc', 'conv3x3_lr_chain': 'conv_chain', 'conv3x3_lr_trunk': 'conv_tc'}
     for k, v in entries.items():
         cap = ncu.get(key.get(k, ''), None)
         v['traffic'] = (cap['traffic'] / (60.0 if k == 'conv3x3_lr_chain' else 1.0)) if cap else None
