@@ -109,6 +109,10 @@ class Network(nn.Module):
         self.overlap_cap = int(os.environ.get('REFVSR_OVERLAP_CAP', _cget(config, 'b200_overlap_cap', 0)))
         self.overlap_main_cap = int(os.environ.get('REFVSR_OVERLAP_MAIN_CAP', _cget(config, 'b200_overlap_main_cap', 0)))
         self.overlap_bw_steps = int(os.environ.get('REFVSR_OVERLAP_BW_STEPS', _cget(config, 'b200_overlap_bw_steps', 0)))
+        # hash-keyed on-disk cache of packed conv weights; opt-in: config.b200_pack_cache = <dir> or
+        # REFVSR_PACK_CACHE=<dir> (packing.py)
+        if _cget(config, 'b200_pack_cache', None):
+            os.environ['REFVSR_PACK_CACHE'] = str(_cget(config, 'b200_pack_cache', None))
         self._side = None
         self._flow_streams = None
         self._ring_mod = None

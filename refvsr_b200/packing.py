@@ -8,11 +8,16 @@ Two layouts (see include/refvsr_b200.h):
            (16-byte chunk j of row r stored at chunk j ^ (r % 8)), so the kernel fetches it with a plain
            bulk copy and hands it to tcgen05.mma unchanged.
 """
+import hashlib
+import os
 from dataclasses import dataclass
 
 import torch
 
 from .lib import IMPL_SIMT, IMPL_TC
+
+with open(__file__, 'rb') as _f:
+    _SELF_DIGEST = hashlib.sha256(_f.read()).digest()
 
 
 @dataclass
@@ -186,7 +191,53 @@ def choose_layout(kh, kw, srcs, nb):
     return forced
 
 
+def _cache_dir():
+    """Directory of the hash-keyed cache of packed layers (one-time repack of a checkpoint), or None.  Opt-in:
+    REFVSR_PACK_CACHE=<dir> (or config.b200_pack_cache through network.py, which sets the same variable)."""
+    d = os.environ.get('REFVSR_PACK_CACHE', '')
+    return d if d not in ('', '0') else None
+
+
+def _pack_key(weight, bias, srcs, stride, pad, act_dtype, prefer_tc, bias_add, tc_layout):
+    """sha256 over the layer's parameters, every packing argument and this file's source (a change of the packing code
+    invalidates the cache by itself); environment switches that steer the layout choice are part of the key."""
+    h = hashlib.sha256()
+    h.update(_SELF_DIGEST)
+    h.update(repr((tuple(weight.shape), str(weight.dtype), [tuple(x) for x in srcs], stride, pad, str(act_dtype), bool(prefer_tc),
+                   float(bias_add), tc_layout, os.environ.get('REFVSR_TC_LAYOUT', ''))).encode())
+    h.update(weight.detach().contiguous().cpu().numpy().tobytes())
+    h.update(bias.detach().float().contiguous().cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
 def pack_conv(name, weight, bias, srcs, stride, pad, act_dtype, device, prefer_tc=True, bias_add=0.0, tc_layout=None):
+    """pack_conv_uncached behind the optional on-disk cache: a hit loads the packed operand image and bias instead of
+    re-deriving them (bit-identical by construction: what is stored is the output of the same function)."""
+    cdir = _cache_dir()
+    if cdir is None:
+        return pack_conv_uncached(name, weight, bias, srcs, stride, pad, act_dtype, device, prefer_tc, bias_add, tc_layout)
+    path = os.path.join(cdir, _pack_key(weight, bias, srcs, stride, pad, act_dtype, prefer_tc, bias_add, tc_layout) + '.pt')
+    if os.path.isfile(path):
+        try:
+            d = torch.load(path, map_location='cpu')
+            return PackedConv(name, d['cout'], d['kh'], d['kw'], d['stride'], d['pad'], d['alloc0'], d['alloc1'], d['impl'], d['nb'],
+                              d['k_real'], d['wpack'].to(device), d['bias'].to(device), d['layout'])
+        except Exception:                       # unreadable / truncated entry: fall through and rewrite it
+            pass
+    pc = pack_conv_uncached(name, weight, bias, srcs, stride, pad, act_dtype, 'cpu', prefer_tc, bias_add, tc_layout)
+    try:
+        os.makedirs(cdir, exist_ok=True)
+        tmp = f'{path}.{os.getpid()}.tmp'
+        torch.save(dict(cout=pc.cout, kh=pc.kh, kw=pc.kw, stride=pc.stride, pad=pc.pad, alloc0=pc.alloc0, alloc1=pc.alloc1,
+                        impl=pc.impl, nb=pc.nb, k_real=pc.k_real, wpack=pc.wpack, bias=pc.bias, layout=pc.layout), tmp)
+        os.replace(tmp, path)                   # atomic: concurrent ranks may pack the same layer
+    except OSError:
+        pass                                    # read-only / full cache directory: the cache is an optimisation only
+    pc.wpack, pc.bias = pc.wpack.to(device), pc.bias.to(device)
+    return pc
+
+
+def pack_conv_uncached(name, weight, bias, srcs, stride, pad, act_dtype, device, prefer_tc=True, bias_add=0.0, tc_layout=None):
     """Pick the implementation and build the packed tensors.  `srcs` = [(real, alloc), ...] (1 or 2)."""
     cout, _, kh, kw = weight.shape
     alloc0 = srcs[0][1]

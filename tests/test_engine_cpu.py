@@ -254,3 +254,35 @@ def test_conv_chain_schedule_is_the_per_layer_schedule(oracle_ops, monkeypatch):
             assert calls['n'] == 0
     for a, b in zip(res[True], res[False]):
         assert torch.equal(a, b)
+
+
+def test_pack_cache_roundtrip(tmp_path, monkeypatch):
+    """hash-keyed on-disk cache of packed conv weights (packing.py): a hit returns the identical operand image,
+    different parameters or packing arguments miss, a corrupt entry is rewritten."""
+    import os
+    from refvsr_b200 import packing
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn((48, 48, 3, 3), generator=g)
+    b = torch.randn((48,), generator=g)
+    ref = packing.pack_conv_uncached('x', w, b, [(48, 48)], 1, 1, torch.bfloat16, 'cpu', True)
+    monkeypatch.setenv('REFVSR_PACK_CACHE', str(tmp_path))
+    a1 = packing.pack_conv('x', w, b, [(48, 48)], 1, 1, torch.bfloat16, 'cpu', True)
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 1 and files[0].endswith('.pt')
+    calls = []
+    orig = packing.pack_conv_uncached
+    monkeypatch.setattr(packing, 'pack_conv_uncached', lambda *a, **k: (calls.append(1), orig(*a, **k))[1])
+    a2 = packing.pack_conv('y', w, b, [(48, 48)], 1, 1, torch.bfloat16, 'cpu', True)
+    assert not calls, 'second pack of the same parameters must come from the cache'
+    for a in (a1, a2):
+        assert torch.equal(a.wpack.view(torch.uint8), ref.wpack.view(torch.uint8)) and torch.equal(a.bias, ref.bias)
+        assert (a.impl, a.nb, a.layout, a.k_real) == (ref.impl, ref.nb, ref.layout, ref.k_real)
+    assert a2.name == 'y'
+    packing.pack_conv('x', w + 1e-3, b, [(48, 48)], 1, 1, torch.bfloat16, 'cpu', True)          # other weights
+    packing.pack_conv('x', w, b, [(48, 48)], 1, 1, torch.float16, 'cpu', True)                  # other dtype
+    packing.pack_conv('x', w, b, [(48, 48)], 1, 1, torch.bfloat16, 'cpu', False)                # SIMT layout
+    assert len(calls) == 3 and len(os.listdir(tmp_path)) == 4
+    with open(os.path.join(tmp_path, files[0]), 'wb') as f:                                       # corrupt entry
+        f.write(b'garbage')
+    a3 = packing.pack_conv('x', w, b, [(48, 48)], 1, 1, torch.bfloat16, 'cpu', True)
+    assert len(calls) == 4 and torch.equal(a3.wpack.view(torch.uint8), ref.wpack.view(torch.uint8))
