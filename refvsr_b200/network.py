@@ -30,6 +30,19 @@ from .modules import build_parameter_tree
 _PREC = {'fp32': torch.float32, 'fp16': torch.float16, 'bf16': torch.bfloat16}
 
 
+class _NewestOnly:
+    """window stand-in of Network.push_frame: only the entering frame (index t-1) exists; the staging loop of _do_window never asks
+    for another one because positions a0 .. a0+t-2 are already staged"""
+
+    def __init__(self, frame, t):
+        self.frame, self.t, self.is_cuda = frame, t, frame.is_cuda
+
+    def __getitem__(self, j):
+        if j != self.t - 1:
+            raise RuntimeError('push_frame: the engine asked for a frame it should already hold (ring bookkeeping out of step)')
+        return self.frame
+
+
 def _cget(config, name, default):
     try:
         v = getattr(config, name)
@@ -674,6 +687,31 @@ class Network(nn.Module):
             if _cget(self.config, 'save_sample', False) and 'eval_vis' in vis:
                 outs['eval_vis'] = vis['eval_vis']
         return outs
+
+    def push_frame(self, lr, ref, b=0):
+        """Streaming entry (a decoded-frame ring buffer feeding the per-frame pipeline): the window slides by one
+        and ONLY the entering frame is handed over - lr (3, h, w), ref (3, hr, wr) in [0, 1], the frame that would have been
+        lrs[b, t-1] / refs[b, t-1] of the next forward() call.  The other t-1 frames are the engine's own staged ring slots, so there
+        is nothing to verify (no reuse-guard launch, no host sync) and the caller moves 1/t of the window's bytes.  Returns the
+        same tensor forward()['result'][b] would: (3, 4h, 4w).  Needs a previous forward() call on this batch slot (the clip's first
+        window, is_first_frame=True); forced resets (reset_branch) follow the same counter as forward()."""
+        if lr.dim() != 3 or ref.dim() != 3 or lr.size(0) != 3 or ref.size(0) != 3:
+            raise ValueError('push_frame takes one LR frame (3, h, w) and one Ref frame (3, hr, wr)')
+        st = self._state.get(b)
+        if st is None or not st.get('has_prev') or not self.reuse:
+            raise RuntimeError('push_frame needs a previous forward() call (the first window of the clip) and b200_reuse=True')
+        t, h, w, hr, wr = st['shape']
+        if tuple(lr.shape[1:]) != (h, w) or tuple(ref.shape[1:]) != (hr, wr) or lr.device != self._device:
+            raise ValueError(f'push_frame: frame shapes / device differ from the running stream {(h, w)} / {(hr, wr)} on {self._device}')
+        is_first_frame = self.max_frame_itr_num is not None and self.frame_itr_num == self.max_frame_itr_num   # RefVSR.py:168-170
+        self._b = b
+        win_lr, win_ref = _NewestOnly(lr, t), _NewestOnly(ref, t)
+        with torch.no_grad():
+            out, _ = self._do_window(b, st, False, win_lr, win_ref, st['shape'], bool(is_first_frame), False, False)
+        if is_first_frame:                                                   # RefVSR.py:292-297
+            self.frame_itr_num = 0
+        self.frame_itr_num += 1
+        return out
 
     def _forward_one(self, b, lrs, refs, is_first_frame, caller_first, is_log, is_train):
         t, _, h, w = lrs.shape

@@ -52,3 +52,8 @@ class SRNet(nn.Module):
 
     def forward(self, x, ref, is_first_frame=True, is_log=False, is_train=False):   # SRNet.py:57-61
         return self.Network.forward(x, ref, is_first_frame, is_log=is_log, is_train=is_train)
+
+    def push_frame(self, lr, ref):
+        """streaming twin of forward() for callers that keep their own decoded-frame ring: after the clip's first window, hand
+        over only the entering (LR, Ref) frame -> (3, 4h, 4w); see Network.push_frame (no counterpart in the reference)"""
+        return self.Network.push_frame(lr, ref)

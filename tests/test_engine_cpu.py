@@ -286,3 +286,33 @@ def test_pack_cache_roundtrip(tmp_path, monkeypatch):
         f.write(b'garbage')
     a3 = packing.pack_conv('x', w, b, [(48, 48)], 1, 1, torch.bfloat16, 'cpu', True)
     assert len(calls) == 4 and torch.equal(a3.wpack.view(torch.uint8), ref.wpack.view(torch.uint8))
+
+
+@pytest.mark.parametrize('name', ['small_t3_32x48', 'small_t7_24x32'])
+def test_push_frame_equals_sliding_windows(name):
+    """Network.push_frame (one entering frame per call, the engine's ring holds the rest) must give exactly what forward() gives
+    for the corresponding sliding window - across steady windows, ring wrap-around and forced resets (reset_branch)."""
+    from oracle.oracle_ops import OracleOps
+    from refvsr_b200.synth import sliding_windows
+    from util import build_case
+    spec, cfg, net, lrs, refs, golden = build_case(name, 'cpu', ops=OracleOps(), b200_precision='fp32')
+    wins = list(sliding_windows(lrs, refs, spec['T']))
+    with torch.no_grad():
+        want = [net(wl, wr, first, False, False)['result'][0].clone() for k, wl, wr, first in wins]
+    spec, cfg, net2, lrs, refs, golden = build_case(name, 'cpu', ops=OracleOps(), b200_precision='fp32')
+    with pytest.raises(RuntimeError, match='previous forward'):
+        net2.push_frame(wins[0][1][0, -1], wins[0][2][0, -1])
+    got = []
+    with torch.no_grad():
+        for k, wl, wr, first in wins:
+            if k == 0:
+                got.append(net2(wl, wr, first, False, False)['result'][0].clone())
+            else:
+                assert not first
+                got.append(net2.push_frame(wl[0, -1], wr[0, -1]).clone())
+    assert len(want) >= 3
+    for k, (a, b) in enumerate(zip(got, want)):
+        assert torch.equal(a, b), f'window {k}: push_frame differs from forward()'
+    assert net2.Network.frame_itr_num == net.Network.frame_itr_num
+    with pytest.raises(ValueError, match='shapes'):
+        net2.push_frame(wins[0][1][0, -1, :, :-2], wins[0][2][0, -1])

@@ -161,6 +161,33 @@ def test_branch_overlap_is_exact():
             assert torch.equal(a, b), f'window {k}: overlapped schedule {key} differs from the sequential one'
 
 
+def test_push_frame_equals_forward_on_gpu():
+    """streaming entry (one entering frame per call, no reuse-guard launch) vs forward() on the sliding windows: bit identical with
+    CUDA graphs, stream overlap, ring wrap-around and forced resets."""
+    from refvsr_b200 import SRNet, get_config
+    from refvsr_b200.modules import seeded_test_weights
+    from refvsr_b200.synth import make_clip, sliding_windows
+    lrs, refs = make_clip(22, 40, 56, 1, seed=11)
+    wins = list(sliding_windows(lrs, refs, 7))
+    outs = {}
+    for mode in ('forward', 'push'):
+        cfg = get_config('RefVSR_MFID', device='cuda', num_blocks=2, b200_precision='bf16')
+        net = SRNet(cfg).eval()
+        seeded_test_weights(net, seed=11)
+        net = net.cuda()
+        res = []
+        for k, wl, wr, first in wins:
+            if mode == 'forward' or k == 0:
+                res.append(net(wl.cuda(), wr.cuda(), first, False, False)['result'][0].cpu())
+            else:
+                res.append(net.push_frame(wl[0, -1].cuda(), wr[0, -1].cuda()).cpu())
+        outs[mode] = res
+        if mode == 'push':
+            assert net.Network.reuse_fallbacks == 0
+    for k, (a, b) in enumerate(zip(outs['push'], outs['forward'])):
+        assert torch.equal(a, b), f'window {k}: push_frame differs from forward()'
+
+
 def test_medium_size_against_oracle():
     """96x128 LR, RefVSR_small_MFID with all 24 blocks, 3 windows: CUDA fp32 path vs the CPU oracle."""
     from oracle.refvsr_oracle import OracleRefVSR
