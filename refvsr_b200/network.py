@@ -15,7 +15,12 @@ confined to *how* results are obtained, never to what they are:
   * every buffer of a step lives at a fixed address (pooled scratch + a ring of T per-frame slots), so a
     whole window is ONE CUDA-graph launch after its first occurrence (~750 kernels, no host work between
     them); graphs are keyed by (ring phase, window kind, work list);
-  * no gc.collect()/empty_cache() (RefVSR.py:206-208), no host synchronisation inside forward.
+  * inside a steady window the branches that do not depend on each other are enqueued on side streams (fork / join nodes of the
+    window's graph): the forward-branch step (RefVSR.py:248-277) and the two optical flows of the entering frame pair run next to
+    the matching / alignment products and the backward branch (RefVSR.py:211-238).  Same kernels, inputs and per-branch order;
+  * `push_frame` (no counterpart in the reference): the window slides by one and only the entering frame is handed over;
+  * no gc.collect()/empty_cache() (RefVSR.py:206-208); the only host synchronisation of a call is the reuse guard's verdict
+    (`b200_reuse_check='sync'`, one int32).
 """
 import collections
 import os
